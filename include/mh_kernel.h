@@ -1,0 +1,167 @@
+/*
+ * mh_kernel.h -- C ABI of libKernel.so, the B200-native drop-in for the reference DLL
+ * `Kernel` (Kernel.vcxproj:22-29).
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes, and never exposes a
+ * CUDA or torch type.  `KernelWrapper` is the one symbol the reference exports
+ * (/root/reference/KernelFolder/Kernel/Kernel.cu:873) and keeps its exact signature;
+ * everything else is additive.
+ *
+ * Error convention: the reference prints, resets the device and calls exit(1) on any CUDA
+ * error (common/inc/helper_cuda.h:985-999).  This library never exits and never resets a
+ * context it does not own: pointer-returning calls return NULL, int-returning calls return
+ * non-zero, and KernelLastError() returns the message for the calling thread.
+ *
+ * There is no CPU fallback: without a CUDA device (or without the sm_100a kernels) every
+ * compute entry point fails.
+ */
+#ifndef MH_KERNEL_H
+#define MH_KERNEL_H
+
+#include "mh_layout.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define MH_API __declspec(dllexport)
+#else
+#define MH_API __attribute__((visibility("default")))
+#endif
+
+/* ---- options for the extended entry points (all additive; zero = reference behaviour) ---- */
+
+enum {
+    MH_SCHEDULE_CONSTANT = 0, /* beta = beta_start for every iteration (reference: BETA = 2.0, Kernel.cu:33) */
+    MH_SCHEDULE_GEOMETRIC = 1, /* beta_i = beta_start * (beta_end/beta_start)^(i/(I-1))                      */
+    MH_SCHEDULE_LINEAR = 2     /* beta_i = beta_start + (beta_end-beta_start) * i/(I-1)                        */
+};
+
+enum {
+    MH_RESULT_FINAL = 0, /* each chain returns its final current layout (Kernel.cu:834-842)             */
+    MH_RESULT_BEST = 1   /* each chain returns the layout with the highest totalCosts it visited; the
+                            reference has this only as dead code (Kernel.cu:779-782, 808-816)            */
+};
+
+enum {
+    MH_EVAL_FULL = 0, /* every proposal re-evaluates every live cost term from scratch (Kernel.cu:804) */
+    MH_EVAL_DELTA = 1 /* reserved: incremental evaluation with periodic full refresh                  */
+};
+
+typedef struct mhOptions {
+    uint32_t struct_size;       /* = sizeof(mhOptions); lets the struct grow compatibly              */
+    uint32_t flags;             /* reserved, 0                                                       */
+    uint64_t seed;              /* Philox key.  KernelWrapper (no options) uses time(NULL) like the
+                                   reference (Kernel.cu:943) unless env MH_SEED is set               */
+    uint64_t chain_offset;      /* global id of this call's first chain: chain g = chain_offset + i
+                                   draws Philox stream g, so a sharded run equals the unsharded one  */
+    uint64_t iteration_offset;  /* first iteration index (resume: continue the same Philox stream)   */
+    double beta_start;          /* 0 -> 2.0                                                          */
+    double beta_end;            /* 0 -> beta_start                                                   */
+    int32_t schedule;           /* MH_SCHEDULE_*                                                     */
+    int32_t schedule_length;    /* iterations over which the schedule runs; 0 -> this call's count   */
+    int32_t result_mode;        /* MH_RESULT_*                                                       */
+    int32_t eval_mode;          /* MH_EVAL_*                                                         */
+    int32_t lanes_per_chain;    /* 0 = choose from nObjs and chain count; else 1,2,4,8,16,32         */
+    int32_t device;             /* CUDA device ordinal; -1 = the caller's current device             */
+    /* parallel tempering (extension; 0 rungs = off).  Chains are grouped in ladders of
+     * `tempering_rungs` consecutive global chain ids; rung r starts at
+     * beta_start * (beta_end/beta_start)^(r/(rungs-1)); every `exchange_interval`
+     * iterations neighbouring rungs exchange their betas with the usual PT acceptance. */
+    int32_t tempering_rungs;
+    int32_t exchange_interval;
+} mhOptions;
+
+/* One record per chain per iteration, for trajectory tests (KernelRunTraced). */
+typedef struct mhTraceEntry {
+    int32_t move;     /* 0 translate, 1 rotate, 2 swap (Kernel.cu:595, 634, 655)       */
+    int32_t obj1;     /* moved object, or first swap partner; -1 if no move was made    */
+    int32_t obj2;     /* second swap partner, else -1                                   */
+    int32_t accepted; /* Accept() outcome (Kernel.cu:819)                               */
+    float star_total; /* totalCosts of the proposal                                     */
+    float cur_total;  /* totalCosts of the current layout AFTER the accept/reject       */
+    float u;          /* the acceptance uniform                                         */
+    float beta;       /* beta used by this iteration                                    */
+} mhTraceEntry;
+MH_STATIC_ASSERT(sizeof(mhTraceEntry) == 32, "mhTraceEntry");
+
+typedef struct mhContext mhContext; /* opaque: device-resident problem + chain state */
+
+/* ---- the reference's entry point -------------------------------------------------------- */
+
+/* Replaces Kernel.cu:873-984.  Array lengths are implicit: rss[R], rsa[R] with
+ * R = srf->nRelationships; cfg[n]; clearances[C]; offlimits[n]; vertices[4C+4n];
+ * surfaceRectangle[4].  Runs gpuCfg->gridxDim chains of gpuCfg->iterations MH steps from
+ * `cfg` and returns a malloc'd array result[gridxDim]; result[i].points points into ONE
+ * malloc'd block of gridxDim*n points whose base is result[0].points (Kernel.cu:928, 970,
+ * 981).  The caller owns both (free() or KernelFree).  Unlike the reference (quirk Q3) the
+ * `costs` of every result are filled in.  NULL on error. */
+MH_API result *KernelWrapper(relationshipStruct *rss, relationshipAngleStruct *rsa,
+                             positionAndRotation *cfg, rectangle *clearances,
+                             rectangle *offlimits, vertex *vertices, vertex *surfaceRectangle,
+                             Surface *srf, gpuConfig *gpuCfg);
+
+/* ---- additive entry points ---------------------------------------------------------------- */
+
+/* KernelWrapper with explicit options (seed, schedule, sharding, best tracking). */
+MH_API result *KernelWrapperEx(const relationshipStruct *rss, const relationshipAngleStruct *rsa,
+                               const positionAndRotation *cfg, const rectangle *clearances,
+                               const rectangle *offlimits, const vertex *vertices,
+                               const vertex *surfaceRectangle, const Surface *srf,
+                               const gpuConfig *gpuCfg, const mhOptions *opt);
+
+/* Frees what KernelWrapper/KernelWrapperEx returned (the reference has no such call and
+ * its only caller leaks; free(res[0].points); free(res) is equivalent). */
+MH_API void KernelFree(result *res);
+
+/* Message of the last failure on the calling thread ("" if none). */
+MH_API const char *KernelLastError(void);
+
+/* Pure cost evaluation on the GPU: the reference's Costs() (Kernel.cu:516-550) applied to
+ * nLayouts layouts of n objects each (layouts[l*n + i]; only x, y, rotY vary in practice,
+ * length/width/frozen are taken from layout 0).  out[nLayouts].  Returns 0 on success. */
+MH_API int KernelEvalCosts(const relationshipStruct *rss, const relationshipAngleStruct *rsa,
+                           const positionAndRotation *layouts, int nLayouts,
+                           const rectangle *clearances, const rectangle *offlimits,
+                           const vertex *vertices, const vertex *surfaceRectangle,
+                           const Surface *srf, resultCosts *out);
+
+/* Persistent, device-resident run: replaces the reference's per-call 12x cudaMalloc, H2D
+ * staging and curand init (Kernel.cu:879-943) for callers that step the same room many
+ * times.  All nChains chains start from `cfg`. */
+MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationshipAngleStruct *rsa,
+                               const positionAndRotation *cfg, const rectangle *clearances,
+                               const rectangle *offlimits, const vertex *vertices,
+                               const vertex *surfaceRectangle, const Surface *srf,
+                               int nChains, const mhOptions *opt);
+/* Advance every chain by `iterations` MH steps (asynchronous on the context's stream). */
+MH_API int KernelRun(mhContext *ctx, int iterations);
+/* Same, and record one mhTraceEntry per chain per iteration: trace[it*nChains + chain]
+ * (host buffer, iterations*nChains entries).  Synchronous. */
+MH_API int KernelRunTraced(mhContext *ctx, int iterations, mhTraceEntry *trace);
+/* Wait for the context's stream. */
+MH_API int KernelSynchronize(mhContext *ctx);
+/* Copy results to host buffers: points[nChains*n], costs[nChains] (either may be NULL). */
+MH_API int KernelResults(mhContext *ctx, point *points, resultCosts *costs);
+/* Device addresses of the result buffers (valid until KernelDestroy), for zero-copy
+ * consumers such as a collective over the per-chain costs. */
+MH_API int KernelDeviceResults(mhContext *ctx, void **d_points, void **d_costs);
+/* Run on a caller-provided CUDA stream (a cudaStream_t passed as void*; NULL = own stream). */
+MH_API int KernelSetStream(mhContext *ctx, void *stream);
+/* Index (local to this context) and totalCosts of the chain with the highest totalCosts
+ * (the sampler maximises totalCosts, quirk Q10); reduced on the device. */
+MH_API int KernelBest(mhContext *ctx, int *bestChain, float *bestTotal);
+/* Milliseconds the device spent in the MH kernels since creation (CUDA events) and how many
+ * kernels were launched. */
+MH_API int KernelStats(mhContext *ctx, double *kernel_ms, long long *launches);
+MH_API void KernelDestroy(mhContext *ctx);
+
+/* Library / device facts for harnesses: returns 0 and fills what is non-NULL. */
+MH_API int KernelDeviceInfo(int *smCount, int *smClockKHz, int *ccMajor, int *ccMinor,
+                            char *name, int nameLen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MH_KERNEL_H */

@@ -1,0 +1,205 @@
+"""ctypes binding of libKernel.so (include/mh_kernel.h).
+
+This is the binding a maintainer of the reference's C# wrapper would write in P/Invoke,
+restated in Python for the tests and bench.py: numpy struct arrays in, numpy struct arrays
+out, every call going through the exported C ABI.  There is no fallback: if the library or a
+CUDA device is missing the call raises KernelError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import layout as L
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_P = C.c_void_p
+
+EXPORTS = ("KernelWrapper", "KernelWrapperEx", "KernelFree", "KernelLastError", "KernelEvalCosts", "KernelCreate", "KernelRun",
+           "KernelRunTraced", "KernelSynchronize", "KernelResults", "KernelDeviceResults", "KernelSetStream", "KernelBest",
+           "KernelStats", "KernelDestroy", "KernelDeviceInfo")
+
+
+class KernelError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libKernel.so")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_P)
+
+
+def make_options(**kw):
+    o = np.zeros(1, L.mhOptions)
+    o["struct_size"] = L.mhOptions.itemsize
+    o["device"] = -1
+    for k, v in kw.items():
+        o[k] = v
+    return o
+
+
+class Kernel:
+    """Loads libKernel.so once and exposes the C ABI."""
+
+    _lib = None
+
+    def __init__(self):
+        if Kernel._lib is None:
+            path = lib_path()
+            if not os.path.exists(path):
+                raise KernelError(f"{path} is missing: build it with `make -C {_HERE}/csrc` (or __graft_entry__.build())")
+            lib = C.CDLL(path)
+            lib.KernelWrapper.restype = _P
+            lib.KernelWrapperEx.restype = _P
+            lib.KernelCreate.restype = _P
+            lib.KernelLastError.restype = C.c_char_p
+            lib.KernelFree.argtypes = [_P]
+            lib.KernelDestroy.argtypes = [_P]
+            lib.KernelRun.argtypes = [_P, C.c_int]
+            lib.KernelRunTraced.argtypes = [_P, C.c_int, _P]
+            lib.KernelSynchronize.argtypes = [_P]
+            lib.KernelResults.argtypes = [_P, _P, _P]
+            lib.KernelSetStream.argtypes = [_P, _P]
+            Kernel._lib = lib
+        self.lib = Kernel._lib
+
+    # ---- helpers -------------------------------------------------------------------------
+    def last_error(self):
+        return (self.lib.KernelLastError() or b"").decode()
+
+    def _fail(self, what):
+        raise KernelError(f"{what}: {self.last_error()}")
+
+    @staticmethod
+    def _room_args(room):
+        return [_ptr(room.rss), _ptr(room.rsa), _ptr(room.cfg), _ptr(room.clearances), _ptr(room.offlimits), _ptr(room.vertices),
+                _ptr(room.surfaceRectangle), _ptr(room.srf)]
+
+    def _unpack(self, res, n_chains, n):
+        r = np.ctypeslib.as_array(C.cast(res, C.POINTER(C.c_uint8)), shape=(n_chains * L.result.itemsize,)).view(L.result)
+        costs = r["costs"].copy()
+        base = int(r["points"][0])
+        # result[i].points must point into ONE block: base + i*n*sizeof(point) (Kernel.cu:981)
+        expect = base + np.arange(n_chains, dtype=np.uint64) * np.uint64(n * L.point.itemsize)
+        if not np.array_equal(r["points"], expect):
+            raise KernelError("result[i].points are not slices of one block")
+        pts = np.ctypeslib.as_array(C.cast(base, C.POINTER(C.c_uint8)), shape=(n_chains * n * L.point.itemsize,)).view(L.point).copy()
+        self.lib.KernelFree(res)
+        return pts.reshape(n_chains, n), costs
+
+    # ---- the reference's entry point -------------------------------------------------------
+    def wrapper(self, room, n_chains, iterations, block=64):
+        """KernelWrapper exactly as the reference's caller invokes it (Kernel.cu:1198)."""
+        g = np.zeros(1, L.gpuConfig)
+        g["gridxDim"], g["blockxDim"], g["iterations"] = n_chains, block, iterations
+        res = self.lib.KernelWrapper(*self._room_args(room), _ptr(g))
+        if not res:
+            self._fail("KernelWrapper")
+        return self._unpack(res, n_chains, room.n)
+
+    def wrapper_ex(self, room, n_chains, iterations, **opts):
+        g = np.zeros(1, L.gpuConfig)
+        g["gridxDim"], g["blockxDim"], g["iterations"] = n_chains, 64, iterations
+        o = make_options(**opts)
+        res = self.lib.KernelWrapperEx(*self._room_args(room), _ptr(g), _ptr(o))
+        if not res:
+            self._fail("KernelWrapperEx")
+        return self._unpack(res, n_chains, room.n)
+
+    def eval_costs(self, room, layouts):
+        n = room.n
+        nl = len(layouts) // n
+        out = np.zeros(nl, L.resultCosts)
+        rc = self.lib.KernelEvalCosts(_ptr(room.rss), _ptr(room.rsa), _ptr(layouts), C.c_int(nl), _ptr(room.clearances),
+                                      _ptr(room.offlimits), _ptr(room.vertices), _ptr(room.surfaceRectangle), _ptr(room.srf), _ptr(out))
+        if rc != 0:
+            self._fail("KernelEvalCosts")
+        return out
+
+    def device_info(self):
+        sm, khz, ma, mi = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        name = C.create_string_buffer(256)
+        if self.lib.KernelDeviceInfo(C.byref(sm), C.byref(khz), C.byref(ma), C.byref(mi), name, 256) != 0:
+            self._fail("KernelDeviceInfo")
+        return {"sm_count": sm.value, "sm_clock_khz": khz.value, "cc": (ma.value, mi.value), "name": name.value.decode()}
+
+    def create(self, room, n_chains, **opts):
+        return Context(self, room, n_chains, **opts)
+
+
+class Context:
+    """Persistent device-resident run (KernelCreate .. KernelDestroy)."""
+
+    def __init__(self, k, room, n_chains, **opts):
+        self.k, self.room, self.n_chains = k, room, n_chains
+        o = make_options(**opts)
+        self.h = k.lib.KernelCreate(*Kernel._room_args(room), C.c_int(n_chains), _ptr(o))
+        if not self.h:
+            k._fail("KernelCreate")
+
+    def run(self, iterations):
+        if self.k.lib.KernelRun(self.h, iterations) != 0:
+            self.k._fail("KernelRun")
+
+    def run_traced(self, iterations):
+        tr = np.zeros(iterations * self.n_chains, L.mhTraceEntry)
+        if self.k.lib.KernelRunTraced(self.h, iterations, _ptr(tr)) != 0:
+            self.k._fail("KernelRunTraced")
+        return tr.reshape(iterations, self.n_chains)
+
+    def synchronize(self):
+        if self.k.lib.KernelSynchronize(self.h) != 0:
+            self.k._fail("KernelSynchronize")
+
+    def results(self, points=None, costs=None):
+        n = self.room.n
+        pts = np.zeros(self.n_chains * n, L.point) if points is None else points
+        cs = np.zeros(self.n_chains, L.resultCosts) if costs is None else costs
+        if self.k.lib.KernelResults(self.h, _ptr(pts), _ptr(cs)) != 0:
+            self.k._fail("KernelResults")
+        return pts.reshape(self.n_chains, n), cs
+
+    def device_results(self):
+        dp, dc = _P(), _P()
+        if self.k.lib.KernelDeviceResults(self.h, C.byref(dp), C.byref(dc)) != 0:
+            self.k._fail("KernelDeviceResults")
+        return dp.value, dc.value
+
+    def set_stream(self, stream_handle):
+        if self.k.lib.KernelSetStream(self.h, _P(stream_handle)) != 0:
+            self.k._fail("KernelSetStream")
+
+    def best(self):
+        i, t = C.c_int(), C.c_float()
+        if self.k.lib.KernelBest(self.h, C.byref(i), C.byref(t)) != 0:
+            self.k._fail("KernelBest")
+        return i.value, t.value
+
+    def stats(self):
+        ms, n = C.c_double(), C.c_longlong()
+        if self.k.lib.KernelStats(self.h, C.byref(ms), C.byref(n)) != 0:
+            self.k._fail("KernelStats")
+        return ms.value, n.value
+
+    def close(self):
+        if self.h:
+            self.k.lib.KernelDestroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,83 @@
+/*
+ * ref_gpu_harness.cu -- the REFERENCE kernel rebuilt for sm_100, plus two probes.
+ *
+ * TEST / BASELINE INFRASTRUCTURE ONLY.  This file #includes the reference translation unit
+ * from /root/reference at build time (oracle/Makefile passes -I to it; nothing is copied);
+ * the output is oracle/_ref/libKernel_ref.so (git-ignored, shipped to the GPU box).
+ *
+ *   KernelWrapper      -- the reference's own entry point, unmodified (Kernel.cu:873).
+ *   RefSetHeap         -- raises cudaLimitMallocHeapSize: the reference kernel malloc()s
+ *                         ~144*n+64 bytes per resident block from an 8 MB default heap
+ *                         (Kernel.cu:771-774; SURVEY.md hard part H3).
+ *   RefCostsGPU        -- the reference's Costs() (Kernel.cu:516) run on the device for a
+ *                         batch of layouts: the GPU cost oracle.
+ *   RefTimedWrapper    -- KernelWrapper bracketed by CUDA events (whole call, on the device
+ *                         clock), for the throughput baseline.
+ */
+#define main ref_main
+#include "Kernel.cu"
+#undef main
+
+__global__ void refCostsKernel(resultCosts *out, Surface *srf, positionAndRotation *layouts, int nLayouts,
+                               relationshipStruct *rs, relationshipAngleStruct *ra, vertex *vertices,
+                               rectangle *clearances, rectangle *offlimits, vertex *surfaceRectangle)
+{
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < nLayouts)
+        Costs(srf, &out[l], layouts + (size_t)l * srf->nObjs, rs, ra, vertices, clearances, offlimits, surfaceRectangle);
+}
+
+template <typename T> static T *up(const T *h, size_t count)
+{
+    T *d = nullptr;
+    if (cudaMalloc(&d, sizeof(T) * (count ? count : 1)) != cudaSuccess) return nullptr;
+    if (count) cudaMemcpy(d, h, sizeof(T) * count, cudaMemcpyHostToDevice);
+    return d;
+}
+
+extern "C" __attribute__((visibility("default"))) int RefSetHeap(size_t bytes)
+{
+    return (int)cudaDeviceSetLimit(cudaLimitMallocHeapSize, bytes);
+}
+
+extern "C" __attribute__((visibility("default")))
+int RefCostsGPU(Surface *srf, positionAndRotation *layouts, int nLayouts, relationshipStruct *rs,
+                relationshipAngleStruct *ra, vertex *vertices, rectangle *clearances, rectangle *offlimits,
+                vertex *surfaceRectangle, resultCosts *out)
+{
+    int n = srf->nObjs, C = srf->nClearances, R = srf->nRelationships;
+    Surface *dS = up(srf, 1);
+    positionAndRotation *dL = up(layouts, (size_t)n * nLayouts);
+    relationshipStruct *dRs = up(rs, R);
+    relationshipAngleStruct *dRa = up(ra, R);
+    vertex *dV = up(vertices, (size_t)4 * (C + n));
+    rectangle *dC = up(clearances, C);
+    rectangle *dO = up(offlimits, n);
+    vertex *dSr = up(surfaceRectangle, 4);
+    resultCosts *dOut = nullptr;
+    cudaMalloc(&dOut, sizeof(resultCosts) * nLayouts);
+    refCostsKernel<<<(nLayouts + 63) / 64, 64>>>(dOut, dS, dL, nLayouts, dRs, dRa, dV, dC, dO, dSr);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, dOut, sizeof(resultCosts) * nLayouts, cudaMemcpyDeviceToHost);
+    cudaFree(dS); cudaFree(dL); cudaFree(dRs); cudaFree(dRa); cudaFree(dV); cudaFree(dC); cudaFree(dO); cudaFree(dSr);
+    cudaFree(dOut);
+    return (int)e;
+}
+
+extern "C" __attribute__((visibility("default")))
+result *RefTimedWrapper(relationshipStruct *rss, relationshipAngleStruct *rsa, positionAndRotation *cfg,
+                        rectangle *clearances, rectangle *offlimits, vertex *vertices, vertex *surfaceRectangle,
+                        Surface *srf, gpuConfig *gpuCfg, float *ms)
+{
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    result *r = KernelWrapper(rss, rsa, cfg, clearances, offlimits, vertices, surfaceRectangle, srf, gpuCfg);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    if (ms) cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return r;
+}
