@@ -1,0 +1,765 @@
+/*
+ * kernel_wrapper.c -- host side of libKernel.so, plain C99.
+ *
+ * Replaces the reference's host wrapper (/root/reference/KernelFolder/Kernel/Kernel.cu:873-984)
+ * and the CUDA-samples helpers it leans on (common/inc/helper_cuda.h): validates the caller's
+ * arrays, packs them into one single-precision problem blob, owns the device-resident chain
+ * state, launches the sm_100a kernels through the thin C ABI of mh_abi.h and assembles the
+ * result block the reference's callers expect.  No CUDA header is included here.
+ *
+ * Differences from the reference that a caller can observe (SURVEY.md quirk ledger):
+ *   Q3  result[i].costs are filled in (the reference returns uninitialised memory);
+ *   Q13 an out-of-range object index is impossible; Q14 an all-frozen layout returns instead of
+ *       spinning; Q15 the seed can be fixed (env MH_SEED or mhOptions.seed);
+ *   Q16 nothing leaks; errors return NULL + KernelLastError() instead of exit(1);
+ *   gpuConfig.blockxDim is accepted and ignored (the launch shape is chosen here).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "../../include/mh_kernel.h"
+#include "mh_abi.h"
+
+#define MH_TLS __thread
+
+static MH_TLS char g_err[512];
+
+static void set_err(const char *fmt, const char *what, int code)
+{
+    if (code)
+        snprintf(g_err, sizeof g_err, fmt, what, mhdev_error_string(code));
+    else
+        snprintf(g_err, sizeof g_err, "%s", what);
+}
+
+#define CU(call)                                                    \
+    do {                                                            \
+        int _e = (call);                                            \
+        if (_e) {                                                   \
+            set_err("%s failed: %s", #call, _e);                    \
+            goto fail;                                              \
+        }                                                           \
+    } while (0)
+
+MH_API const char *KernelLastError(void) { return g_err; }
+
+/* ---------------------------------------------------------------------------------------------
+ * Problem packing
+ * --------------------------------------------------------------------------------------------- */
+
+static float below_or_equal(double v) /* largest float <= v */
+{
+    float f = (float)v;
+    if ((double)f > v)
+        f = nextafterf(f, -INFINITY);
+    return f;
+}
+
+static int align4(int w) { return (w + 3) & ~3; }
+
+typedef struct mhProblem {
+    float *blob; /* host copy */
+    mhProblemHeader *h;
+} mhProblem;
+
+static int check_rect(const rectangle *r, int nverts, const char *what, int idx)
+{
+    if (r->point1Index < 0 || r->point1Index + 3 >= nverts) {
+        snprintf(g_err, sizeof g_err, "%s[%d].point1Index = %d: needs 4 consecutive vertices inside vertices[%d]", what, idx,
+                 r->point1Index, nverts);
+        return -1;
+    }
+    return 0;
+}
+
+/* AABB constants of the four consecutive vertices from `start` (Kernel.cu:366-401 hoisted). */
+static void rect_consts(const vertex *v, int start, float box[4], float *v0x)
+{
+    double m123x = fmin(v[start + 1].x, fmin(v[start + 2].x, v[start + 3].x));
+    double miny = fmin(fmin(v[start].y, v[start + 1].y), fmin(v[start + 2].y, v[start + 3].y));
+    double maxx = fmax(fmax(v[start].x, v[start + 1].x), fmax(v[start + 2].x, v[start + 3].x));
+    double maxy = fmax(fmax(v[start].y, v[start + 1].y), fmax(v[start + 2].y, v[start + 3].y));
+    box[0] = (float)m123x;
+    box[1] = (float)miny;
+    box[2] = (float)maxx;
+    box[3] = (float)maxy;
+    *v0x = (float)v[start].x; /* quirk Q6 */
+}
+
+static int pack_problem(const relationshipStruct *rss, const relationshipAngleStruct *rsa, const positionAndRotation *cfg,
+                        const rectangle *clearances, const rectangle *offlimits, const vertex *vertices,
+                        const vertex *surfaceRectangle, const Surface *srf, mhProblem *out)
+{
+    out->blob = NULL;
+    if (!srf || !cfg || !offlimits || !vertices || !surfaceRectangle) {
+        set_err("", "null argument", 0);
+        return -1;
+    }
+    const int n = srf->nObjs, C = srf->nClearances, R = srf->nRelationships;
+    if (n < 1 || C < 0 || R < 0 || n > 65535) {
+        snprintf(g_err, sizeof g_err, "bad counts: nObjs=%d nClearances=%d nRelationships=%d", n, C, R);
+        return -1;
+    }
+    if (C > n) { /* quirk Q7: SurfaceAreaCosts reads cfg[i] for every clearance i */
+        snprintf(g_err, sizeof g_err, "nClearances (%d) > nObjs (%d): the reference reads cfg[i] for clearance i", C, n);
+        return -1;
+    }
+    if ((C > 0 && !clearances) || (R > 0 && (!rss || !rsa))) {
+        set_err("", "null argument", 0);
+        return -1;
+    }
+    const int nverts = 4 * C + 4 * n;
+    for (int i = 0; i < n; i++)
+        if (check_rect(&offlimits[i], nverts, "offlimits", i)) return -1;
+    for (int i = 0; i < C; i++) {
+        if (check_rect(&clearances[i], nverts, "clearances", i)) return -1;
+        if (clearances[i].SourceIndex < 0 || clearances[i].SourceIndex >= n) {
+            snprintf(g_err, sizeof g_err, "clearances[%d].SourceIndex = %d out of range", i, clearances[i].SourceIndex);
+            return -1;
+        }
+    }
+    for (int i = 0; i < R; i++) {
+        if (rss[i].SourceIndex < 0 || rss[i].SourceIndex >= n || rss[i].TargetIndex < 0 || rss[i].TargetIndex >= n ||
+            rsa[i].SourceIndex < 0 || rsa[i].SourceIndex >= n || rsa[i].TargetIndex < 0 || rsa[i].TargetIndex >= n) {
+            snprintf(g_err, sizeof g_err, "relationship %d: object index out of range", i);
+            return -1;
+        }
+    }
+
+    const int hw = align4((int)(sizeof(mhProblemHeader) / 4));
+    int w = hw;
+    mhProblemHeader H;
+    memset(&H, 0, sizeof H);
+    H.off_obj_box = w;    w += 4 * n;
+    H.off_clr_box = w;    w += 4 * C;
+    H.off_rel_rng = w;    w += 4 * R;
+    H.off_rel_aux = w;    w += 4 * R;
+    H.off_rel_idx = w;    w += 4 * R;
+    H.off_obj_v0x = w;    w = align4(w + n);
+    H.off_obj_area = w;   w = align4(w + n);
+    H.off_obj_frozen = w; w = align4(w + n);
+    H.off_clr_v0x = w;    w = align4(w + C);
+    H.off_clr_src = w;    w = align4(w + C);
+    H.smem_words = w;
+    H.off_cfg0 = w;       w = align4(w + 3 * n);
+    H.off_pass = w;       w = align4(w + 3 * n);
+    H.total_words = w;
+
+    float *b = (float *)calloc((size_t)w, sizeof(float));
+    if (!b) {
+        set_err("", "out of host memory", 0);
+        return -1;
+    }
+    int32_t *bi = (int32_t *)b;
+
+    H.n = n; H.C = C; H.R = R;
+    H.w_focal = srf->WeightFocalPoint; H.w_pair = srf->WeightPairWise; H.w_visual = srf->WeightVisualBalance;
+    H.w_sym = srf->WeightSymmetry; H.w_off = srf->WeightOffLimits; H.w_clear = srf->WeightClearance;
+    H.w_surf = srf->WeightSurfaceArea;
+    H.focal_x = (float)srf->focalX; H.focal_y = (float)srf->focalY;
+    H.ux = (float)cos(srf->focalRot); H.uy = (float)sin(srf->focalRot);          /* Kernel.cu:290-291 */
+    H.fdotu = (float)(srf->focalX * H.ux + srf->focalY * H.uy);                  /* Kernel.cu:292 */
+    H.two_focal_rot = (float)(2 * srf->focalRot);                               /* Kernel.cu:297 */
+    H.cx2 = (float)(srf->centroidX / 2); H.cy2 = (float)(srf->centroidY / 2);   /* Kernel.cu:206, Q11 */
+    {   /* room AABB: minValue/maxValue(surfaceRectangle, 0, 0, 0), Kernel.cu:585-591 */
+        double x0 = surfaceRectangle[0].x, x1 = x0, y0 = surfaceRectangle[0].y, y1 = y0;
+        for (int k = 1; k < 4; k++) {
+            x0 = fmin(x0, surfaceRectangle[k].x); x1 = fmax(x1, surfaceRectangle[k].x);
+            y0 = fmin(y0, surfaceRectangle[k].y); y1 = fmax(y1, surfaceRectangle[k].y);
+        }
+        H.room_minx = (float)x0; H.room_miny = (float)y0; H.room_maxx = (float)x1; H.room_maxy = (float)y1;
+        float width = (float)(x1 - x0), height = (float)(y1 - y0);
+        H.std_x = width / 16; H.std_y = height / 16;                            /* Q19 */
+    }
+    H.sigma_t = (float)MH_S_SIGMA_T;
+    H.pi_cmp = below_or_equal(MH_PI);
+    H.two_pi = (float)(2 * MH_PI);
+    H.two_pi_cmp = below_or_equal(2 * MH_PI);
+    H.half_pi = (float)(MH_PI / 2.0);
+
+    float denom = 0.f;
+    int any_free = 0;
+    for (int i = 0; i < n; i++) {
+        rect_consts(vertices, offlimits[i].point1Index, b + H.off_obj_box + 4 * i, b + H.off_obj_v0x + i);
+        float area = (float)(cfg[i].length * cfg[i].width);                     /* Kernel.cu:199 */
+        b[H.off_obj_area + i] = area;
+        denom += area;
+        bi[H.off_obj_frozen + i] = cfg[i].frozen ? 1 : 0;
+        any_free |= !cfg[i].frozen;
+        b[H.off_cfg0 + i] = (float)cfg[i].x;
+        b[H.off_cfg0 + n + i] = (float)cfg[i].y;
+        b[H.off_cfg0 + 2 * n + i] = (float)cfg[i].rotY;
+        b[H.off_pass + i] = (float)cfg[i].z;
+        b[H.off_pass + n + i] = (float)cfg[i].rotX;
+        b[H.off_pass + 2 * n + i] = (float)cfg[i].rotZ;
+    }
+    H.denom = denom;
+    H.any_free = any_free;
+    for (int i = 0; i < C; i++) {
+        rect_consts(vertices, clearances[i].point1Index, b + H.off_clr_box + 4 * i, b + H.off_clr_v0x + i);
+        bi[H.off_clr_src + i] = clearances[i].SourceIndex;
+    }
+    for (int i = 0; i < R; i++) {
+        /* Kernel.cu:216, 243: the r-th distance relation uses rss[r]'s pair, the r-th angle
+         * relation rsa[r]'s pair (callers make them equal, but nothing requires it) */
+        bi[H.off_rel_idx + 4 * i] = rss[i].SourceIndex;
+        bi[H.off_rel_idx + 4 * i + 1] = rss[i].TargetIndex;
+        bi[H.off_rel_idx + 4 * i + 2] = rsa[i].SourceIndex;
+        bi[H.off_rel_idx + 4 * i + 3] = rsa[i].TargetIndex;
+        const double start = rss[i].TargetRange.targetRangeStart, end = rss[i].TargetRange.targetRangeEnd;
+        const double amin = rsa[i].angleMin, amax = rsa[i].angleMax;
+        const int wraps = amin > amax;                                          /* Kernel.cu:245 */
+        const double norm = wraps ? (2 * MH_PI - (amax + (2 * MH_PI - amin))) / 2.0 /* Kernel.cu:246 */
+                                  : (2 * MH_PI - (amax - amin)) / 2.0;              /* Kernel.cu:252 */
+        float *rng = b + H.off_rel_rng + 4 * i, *aux = b + H.off_rel_aux + 4 * i;
+        rng[0] = (float)(1.0 / start); rng[1] = (float)end; rng[2] = (float)amin; rng[3] = (float)amax;
+        aux[0] = (float)start; aux[1] = (float)(1.0 / norm); aux[2] = wraps ? 1.f : 0.f; aux[3] = 0.f;
+    }
+    memcpy(b, &H, sizeof H);
+    out->blob = b;
+    out->h = (mhProblemHeader *)b;
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Context
+ * --------------------------------------------------------------------------------------------- */
+
+typedef struct evPair { void *e0, *e1; } evPair;
+
+struct mhContext {
+    int device;        /* device the context lives on */
+    int n, C, R, n_chains, lanes, score_lanes;
+    mhOptions opt;
+    int problem_words, smem_words;
+    void *d_problem;
+    float *d_x, *d_y, *d_rot, *d_cur, *d_best, *d_beta;
+    uint16_t *d_perm;
+    void *d_points, *d_costs, *d_scratch;
+    void *stream;
+    int own_stream;
+    uint64_t it_done;  /* iterations already run (relative to opt.iteration_offset) */
+    int fresh, costs_dirty;
+    evPair *ev; int n_ev, cap_ev;
+    double kernel_ms; long long launches;
+};
+
+static int enter_device(int want, int *prev)
+{
+    int e = mhdev_get_device(prev);
+    if (e) return e;
+    if (want >= 0 && want != *prev) return mhdev_set_device(want);
+    return 0;
+}
+static void leave_device(int want, int prev)
+{
+    if (want >= 0 && want != prev) mhdev_set_device(prev);
+}
+
+/* Lanes per chain.  Fewer lanes waste fewer slots of the last row pass (efficiency
+ * n / (G*ceil(n/G))) but put more chains, hence more shared memory, behind every warp and need
+ * more chains to fill the machine.  Score = lane efficiency x how well the resident warps cover
+ * the SMs; see DESIGN.md for the measured table behind the constants. */
+static int choose_lanes(int n, int C, int smem_words, int n_chains, int requested)
+{
+    int max_block = 0, max_sm = 0, sms = 0;
+    if (mhdev_device_limits(&max_block, &max_sm, &sms, NULL, NULL, NULL, NULL, 0)) return -1;
+    const char *env = getenv("MH_LANES");
+    if (requested <= 0 && env) requested = atoi(env);
+    static const int cand[6] = { 32, 16, 8, 4, 2, 1 };
+    int best = -1;
+    double best_score = -1.0;
+    for (int k = 0; k < 6; k++) {
+        const int G = cand[k];
+        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, G, 0);
+        if (bytes < 0 || bytes > max_block) continue;
+        if (requested == G) return G;
+        int blocks_per_sm = max_sm / (bytes + 1024);
+        if (blocks_per_sm > 5) blocks_per_sm = 5; /* register-limited: ~96 regs x 128 threads */
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        const double cap_warps = 4.0 * blocks_per_sm;
+        const double cpw = 32.0 / G;
+        const double warps_total = ceil((double)n_chains / cpw);
+        double per_sm = warps_total / (double)sms;
+        if (per_sm > cap_warps) per_sm = cap_warps;
+        const double cover = per_sm >= 12.0 ? 1.0 : per_sm / 12.0;
+        const double rows = ceil((double)n / G);
+        const double eff = (double)n / (G * rows);
+        const double score = eff * cover;
+        if (score > best_score * 1.02) { /* ties go to the wider group (less shared memory) */
+            best_score = score;
+            best = G;
+        }
+    }
+    if (best < 0) snprintf(g_err, sizeof g_err, "problem does not fit in shared memory (n=%d, C=%d)", n, C);
+    return best;
+}
+
+static void ctx_free(mhContext *c)
+{
+    if (!c) return;
+    mhdev_free(c->d_problem); mhdev_free(c->d_x); mhdev_free(c->d_y); mhdev_free(c->d_rot); mhdev_free(c->d_cur);
+    mhdev_free(c->d_best); mhdev_free(c->d_beta); mhdev_free(c->d_perm); mhdev_free(c->d_points); mhdev_free(c->d_costs);
+    mhdev_free(c->d_scratch);
+    for (int i = 0; i < c->n_ev; i++) { mhdev_event_destroy(c->ev[i].e0); mhdev_event_destroy(c->ev[i].e1); }
+    free(c->ev);
+    if (c->own_stream) mhdev_stream_destroy(c->stream);
+    free(c);
+}
+
+static void default_options(mhOptions *o)
+{
+    memset(o, 0, sizeof *o);
+    o->struct_size = (uint32_t)sizeof *o;
+    o->device = -1;
+}
+
+static void take_options(mhOptions *dst, const mhOptions *src)
+{
+    default_options(dst);
+    if (src) {
+        size_t sz = src->struct_size ? src->struct_size : sizeof *src;
+        if (sz > sizeof *dst) sz = sizeof *dst;
+        memcpy(dst, src, sz);
+        dst->struct_size = (uint32_t)sizeof *dst;
+    }
+    if (dst->beta_start <= 0) dst->beta_start = MH_BETA;
+    if (dst->beta_end <= 0) dst->beta_end = dst->beta_start;
+}
+
+MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationshipAngleStruct *rsa,
+                               const positionAndRotation *cfg, const rectangle *clearances, const rectangle *offlimits,
+                               const vertex *vertices, const vertex *surfaceRectangle, const Surface *srf, int nChains,
+                               const mhOptions *opt)
+{
+    g_err[0] = 0;
+    mhProblem P;
+    mhContext *c = NULL;
+    int prev = -1, entered = 0;
+    if (nChains < 1) {
+        set_err("", "nChains must be >= 1", 0);
+        return NULL;
+    }
+    if (pack_problem(rss, rsa, cfg, clearances, offlimits, vertices, surfaceRectangle, srf, &P)) return NULL;
+    c = (mhContext *)calloc(1, sizeof *c);
+    if (!c) { set_err("", "out of host memory", 0); goto fail; }
+    take_options(&c->opt, opt);
+    if (c->opt.tempering_rungs > 1) {
+        if (nChains % c->opt.tempering_rungs || c->opt.chain_offset % (uint64_t)c->opt.tempering_rungs) {
+            set_err("", "tempering: chain_offset and nChains must be multiples of tempering_rungs", 0);
+            goto fail;
+        }
+        if (c->opt.exchange_interval <= 0) c->opt.exchange_interval = 100;
+    }
+    c->device = c->opt.device;
+    CU(enter_device(c->device, &prev));
+    entered = 1;
+    if (c->device < 0) c->device = prev;
+    c->n = P.h->n; c->C = P.h->C; c->R = P.h->R; c->n_chains = nChains;
+    c->problem_words = P.h->total_words; c->smem_words = P.h->smem_words;
+    c->lanes = choose_lanes(c->n, c->C, c->smem_words, nChains, c->opt.lanes_per_chain);
+    if (c->lanes < 0) goto fail;
+    c->score_lanes = c->lanes;
+    c->fresh = 1;
+    CU(mhdev_stream_create(&c->stream));
+    c->own_stream = 1;
+    const size_t cn = (size_t)nChains * (size_t)c->n;
+    CU(mhdev_malloc(&c->d_problem, 4 * (size_t)c->problem_words));
+    CU(mhdev_malloc((void **)&c->d_x, 4 * cn));
+    CU(mhdev_malloc((void **)&c->d_y, 4 * cn));
+    CU(mhdev_malloc((void **)&c->d_rot, 4 * cn));
+    CU(mhdev_malloc((void **)&c->d_perm, 2 * cn));
+    CU(mhdev_malloc((void **)&c->d_cur, 4 * (size_t)nChains));
+    CU(mhdev_malloc((void **)&c->d_best, 4 * (size_t)nChains));
+    CU(mhdev_malloc((void **)&c->d_beta, 4 * (size_t)nChains));
+    CU(mhdev_malloc(&c->d_points, sizeof(point) * cn));
+    CU(mhdev_malloc(&c->d_costs, sizeof(resultCosts) * (size_t)nChains));
+    CU(mhdev_malloc(&c->d_scratch, 64));
+    CU(mhdev_h2d(c->d_problem, P.blob, 4 * (size_t)c->problem_words, c->stream));
+    if (c->opt.tempering_rungs > 1) {
+        /* rung r of every ladder starts at beta_start * (beta_end/beta_start)^(r/(T-1)) */
+        const int T = c->opt.tempering_rungs;
+        float *hb = (float *)malloc(4 * (size_t)nChains);
+        if (!hb) { set_err("", "out of host memory", 0); goto fail; }
+        const float lr = log2f((float)(c->opt.beta_end / c->opt.beta_start));
+        for (int i = 0; i < nChains; i++) {
+            const int r = (int)((c->opt.chain_offset + (uint64_t)i) % (uint64_t)T);
+            const float t = T > 1 ? (float)r / (float)(T - 1) : 0.f;
+            hb[i] = (float)c->opt.beta_start * exp2f(t * lr);
+        }
+        int e = mhdev_h2d(c->d_beta, hb, 4 * (size_t)nChains, c->stream);
+        if (!e) e = mhdev_stream_sync(c->stream);
+        free(hb);
+        CU(e);
+    }
+    CU(mhdev_stream_sync(c->stream)); /* the blob is freed below */
+    free(P.blob);
+    leave_device(c->opt.device, prev);
+    return c;
+fail:
+    free(P.blob);
+    if (c) ctx_free(c);
+    if (entered) leave_device(opt ? opt->device : -1, prev);
+    return NULL;
+}
+
+static int push_events(mhContext *c, void **e0, void **e1)
+{
+    if (c->n_ev == c->cap_ev) {
+        int cap = c->cap_ev ? 2 * c->cap_ev : 16;
+        evPair *p = (evPair *)realloc(c->ev, sizeof(evPair) * (size_t)cap);
+        if (!p) return -1;
+        c->ev = p;
+        c->cap_ev = cap;
+    }
+    int e = mhdev_event_create(e0);
+    if (e) return e;
+    e = mhdev_event_create(e1);
+    if (e) return e;
+    c->ev[c->n_ev].e0 = *e0;
+    c->ev[c->n_ev].e1 = *e1;
+    c->n_ev++;
+    return 0;
+}
+
+static int drain_events(mhContext *c)
+{
+    for (int i = 0; i < c->n_ev; i++) {
+        float ms = 0.f;
+        int e = mhdev_event_elapsed_ms(c->ev[i].e0, c->ev[i].e1, &ms);
+        if (e) return e;
+        c->kernel_ms += ms;
+        mhdev_event_destroy(c->ev[i].e0);
+        mhdev_event_destroy(c->ev[i].e1);
+    }
+    c->n_ev = 0;
+    return 0;
+}
+
+static int launch_segment(mhContext *c, int iterations, void *d_trace)
+{
+    mhLaunch L;
+    memset(&L, 0, sizeof L);
+    L.d_problem = c->d_problem; L.problem_words = c->problem_words; L.smem_words = c->smem_words;
+    L.n = c->n; L.C = c->C; L.R = c->R; L.n_chains = c->n_chains; L.lanes = c->lanes; L.fresh = c->fresh;
+    L.seed = c->opt.seed; L.chain_offset = c->opt.chain_offset; L.chain_stride = 1;
+    L.it_begin = c->opt.iteration_offset + c->it_done; L.it_count = iterations;
+    L.schedule = c->opt.tempering_rungs > 1 ? MH_SCHED_PER_CHAIN : c->opt.schedule;
+    L.schedule_length = c->opt.schedule_length;
+    L.result_mode = c->opt.result_mode;
+    L.beta_start = (float)c->opt.beta_start; L.beta_end = (float)c->opt.beta_end;
+    L.beta_log2_ratio = log2f((float)(c->opt.beta_end / c->opt.beta_start));
+    L.d_x = c->d_x; L.d_y = c->d_y; L.d_rot = c->d_rot; L.d_perm = c->d_perm; L.d_cur_total = c->d_cur;
+    L.d_best_total = c->d_best; L.d_beta = c->d_beta; L.d_points = c->d_points; L.d_costs = c->d_costs; L.d_trace = d_trace;
+    L.stream = c->stream;
+    void *e0 = NULL, *e1 = NULL;
+    int e = push_events(c, &e0, &e1);
+    if (e) return e;
+    e = mhdev_event_record(e0, c->stream);
+    if (e) return e;
+    e = mhdev_launch_chains(&L);
+    if (e) return e;
+    e = mhdev_event_record(e1, c->stream);
+    if (e) return e;
+    c->launches++;
+    c->fresh = 0;
+    c->it_done += (uint64_t)iterations;
+    c->costs_dirty = 1;
+    if (c->n_ev >= 1024) return drain_events(c);
+    return 0;
+}
+
+static int run_iterations(mhContext *c, int iterations, mhTraceEntry *trace)
+{
+    void *d_trace = NULL;
+    int prev = -1, rc = -1;
+    g_err[0] = 0;
+    if (!c || iterations < 0) { set_err("", "bad arguments", 0); return -1; }
+    CU(enter_device(c->device, &prev));
+    if (c->opt.schedule_length <= 0 && c->opt.schedule != MH_SCHEDULE_CONSTANT) c->opt.schedule_length = iterations;
+    if (trace) CU(mhdev_malloc(&d_trace, sizeof(mhTraceEntry) * (size_t)iterations * (size_t)c->n_chains));
+    if (c->opt.tempering_rungs > 1) {
+        /* segments end on exchange boundaries; the whole ladder lives in this context */
+        const uint64_t ex = (uint64_t)c->opt.exchange_interval;
+        int left = iterations;
+        size_t traced = 0;
+        while (left > 0) {
+            const uint64_t git = c->opt.iteration_offset + c->it_done;
+            uint64_t to_boundary = ex - (git % ex);
+            int seg = left < (int)to_boundary ? left : (int)to_boundary;
+            CU(launch_segment(c, seg, d_trace ? (char *)d_trace + sizeof(mhTraceEntry) * traced * (size_t)c->n_chains : NULL));
+            traced += (size_t)seg;
+            left -= seg;
+            const uint64_t gnow = c->opt.iteration_offset + c->it_done;
+            if (gnow % ex == 0) {
+                CU(mhdev_launch_exchange(c->n_chains, c->opt.chain_offset, 1, c->opt.tempering_rungs, gnow / ex, gnow - 1,
+                                         c->opt.seed, c->d_cur, c->d_beta, c->opt.chain_offset, c->d_beta, c->stream));
+                c->launches++;
+            }
+        }
+    } else if (iterations > 0 || c->fresh) {
+        CU(launch_segment(c, iterations, d_trace));
+    }
+    if (trace) {
+        CU(mhdev_d2h(trace, d_trace, sizeof(mhTraceEntry) * (size_t)iterations * (size_t)c->n_chains, c->stream));
+        CU(mhdev_stream_sync(c->stream));
+    }
+    rc = 0;
+fail:
+    if (d_trace) { mhdev_stream_sync(c->stream); mhdev_free(d_trace); }
+    if (prev >= 0) leave_device(c->device, prev);
+    return rc;
+}
+
+MH_API int KernelRun(mhContext *ctx, int iterations) { return run_iterations(ctx, iterations, NULL); }
+
+MH_API int KernelRunTraced(mhContext *ctx, int iterations, mhTraceEntry *trace)
+{
+    if (!trace) { set_err("", "trace buffer is NULL", 0); return -1; }
+    return run_iterations(ctx, iterations, trace);
+}
+
+static int ensure_scored(mhContext *c)
+{
+    if (c->fresh) { /* nothing has run: emit the initial layout */
+        int e = launch_segment(c, 0, NULL);
+        if (e) return e;
+    }
+    if (!c->costs_dirty) return 0;
+    int e = mhdev_launch_score(c->d_problem, c->smem_words, c->n, c->C, c->R, c->n_chains, c->score_lanes, c->d_points, c->d_costs,
+                               c->stream);
+    if (e) return e;
+    c->launches++;
+    c->costs_dirty = 0;
+    return 0;
+}
+
+MH_API int KernelSynchronize(mhContext *ctx)
+{
+    int prev = -1, rc = -1;
+    g_err[0] = 0;
+    if (!ctx) { set_err("", "null context", 0); return -1; }
+    CU(enter_device(ctx->device, &prev));
+    CU(mhdev_stream_sync(ctx->stream));
+    rc = 0;
+fail:
+    if (prev >= 0) leave_device(ctx->device, prev);
+    return rc;
+}
+
+MH_API int KernelResults(mhContext *ctx, point *points, resultCosts *costs)
+{
+    int prev = -1, rc = -1;
+    g_err[0] = 0;
+    if (!ctx) { set_err("", "null context", 0); return -1; }
+    CU(enter_device(ctx->device, &prev));
+    CU(ensure_scored(ctx));
+    if (points) CU(mhdev_d2h(points, ctx->d_points, sizeof(point) * (size_t)ctx->n_chains * (size_t)ctx->n, ctx->stream));
+    if (costs) CU(mhdev_d2h(costs, ctx->d_costs, sizeof(resultCosts) * (size_t)ctx->n_chains, ctx->stream));
+    CU(mhdev_stream_sync(ctx->stream));
+    rc = 0;
+fail:
+    if (prev >= 0) leave_device(ctx->device, prev);
+    return rc;
+}
+
+MH_API int KernelDeviceResults(mhContext *ctx, void **d_points, void **d_costs)
+{
+    int prev = -1, rc = -1;
+    g_err[0] = 0;
+    if (!ctx) { set_err("", "null context", 0); return -1; }
+    CU(enter_device(ctx->device, &prev));
+    CU(ensure_scored(ctx));
+    if (d_points) *d_points = ctx->d_points;
+    if (d_costs) *d_costs = ctx->d_costs;
+    rc = 0;
+fail:
+    if (prev >= 0) leave_device(ctx->device, prev);
+    return rc;
+}
+
+MH_API int KernelSetStream(mhContext *ctx, void *stream)
+{
+    g_err[0] = 0;
+    if (!ctx) { set_err("", "null context", 0); return -1; }
+    if (KernelSynchronize(ctx)) return -1;
+    if (ctx->own_stream) {
+        int prev = -1;
+        if (!enter_device(ctx->device, &prev)) {
+            mhdev_stream_destroy(ctx->stream);
+            leave_device(ctx->device, prev);
+        }
+        ctx->own_stream = 0;
+    }
+    ctx->stream = stream;
+    if (!stream) {
+        int prev = -1, e = enter_device(ctx->device, &prev);
+        if (!e) e = mhdev_stream_create(&ctx->stream);
+        if (prev >= 0) leave_device(ctx->device, prev);
+        if (e) { set_err("%s failed: %s", "stream create", e); return -1; }
+        ctx->own_stream = 1;
+    }
+    return 0;
+}
+
+MH_API int KernelBest(mhContext *ctx, int *bestChain, float *bestTotal)
+{
+    int prev = -1, rc = -1;
+    struct { float total; int32_t idx; } h = { 0.f, -1 };
+    g_err[0] = 0;
+    if (!ctx) { set_err("", "null context", 0); return -1; }
+    CU(enter_device(ctx->device, &prev));
+    CU(ensure_scored(ctx));
+    CU(mhdev_launch_argmax(ctx->d_costs, ctx->n_chains, ctx->d_scratch, ctx->stream));
+    ctx->launches++;
+    CU(mhdev_d2h(&h, ctx->d_scratch, sizeof h, ctx->stream));
+    CU(mhdev_stream_sync(ctx->stream));
+    if (bestChain) *bestChain = h.idx;
+    if (bestTotal) *bestTotal = h.total;
+    rc = 0;
+fail:
+    if (prev >= 0) leave_device(ctx->device, prev);
+    return rc;
+}
+
+MH_API int KernelStats(mhContext *ctx, double *kernel_ms, long long *launches)
+{
+    int prev = -1, rc = -1;
+    g_err[0] = 0;
+    if (!ctx) { set_err("", "null context", 0); return -1; }
+    CU(enter_device(ctx->device, &prev));
+    CU(drain_events(ctx));
+    if (kernel_ms) *kernel_ms = ctx->kernel_ms;
+    if (launches) *launches = ctx->launches;
+    rc = 0;
+fail:
+    if (prev >= 0) leave_device(ctx->device, prev);
+    return rc;
+}
+
+MH_API void KernelDestroy(mhContext *ctx)
+{
+    if (!ctx) return;
+    int prev = -1;
+    const int dev = ctx->device;
+    int e = enter_device(dev, &prev);
+    if (!e) mhdev_stream_sync(ctx->stream);
+    ctx_free(ctx);
+    if (prev >= 0) leave_device(dev, prev);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * One-shot entry points
+ * --------------------------------------------------------------------------------------------- */
+
+MH_API result *KernelWrapperEx(const relationshipStruct *rss, const relationshipAngleStruct *rsa,
+                               const positionAndRotation *cfg, const rectangle *clearances, const rectangle *offlimits,
+                               const vertex *vertices, const vertex *surfaceRectangle, const Surface *srf,
+                               const gpuConfig *gpuCfg, const mhOptions *opt)
+{
+    g_err[0] = 0;
+    if (!gpuCfg || !srf) { set_err("", "null argument", 0); return NULL; }
+    const int chains = gpuCfg->gridxDim, iterations = gpuCfg->iterations;
+    if (chains < 1 || iterations < 0) {
+        snprintf(g_err, sizeof g_err, "bad gpuConfig: gridxDim=%d iterations=%d", chains, iterations);
+        return NULL;
+    }
+    const int n = srf->nObjs;
+    mhContext *c = KernelCreate(rss, rsa, cfg, clearances, offlimits, vertices, surfaceRectangle, srf, chains, opt);
+    if (!c) return NULL;
+    /* Kernel.cu:928, 970: ONE block of points and one array of results, both plain malloc */
+    point *pts = (point *)malloc(sizeof(point) * (size_t)chains * (size_t)n);
+    result *res = (result *)malloc(sizeof(result) * (size_t)chains);
+    resultCosts *costs = (resultCosts *)malloc(sizeof(resultCosts) * (size_t)chains);
+    if (!pts || !res || !costs) { set_err("", "out of host memory", 0); goto fail; }
+    if (KernelRun(c, iterations)) goto fail;
+    if (KernelResults(c, pts, costs)) goto fail;
+    for (int i = 0; i < chains; i++) {
+        res[i].points = pts + (size_t)i * (size_t)n; /* Kernel.cu:981 */
+        res[i].costs = costs[i];
+    }
+    free(costs);
+    KernelDestroy(c);
+    return res;
+fail:
+    free(pts); free(res); free(costs);
+    {   /* keep the message across the clean-up */
+        char keep[sizeof g_err];
+        memcpy(keep, g_err, sizeof keep);
+        KernelDestroy(c);
+        memcpy(g_err, keep, sizeof keep);
+    }
+    return NULL;
+}
+
+MH_API result *KernelWrapper(relationshipStruct *rss, relationshipAngleStruct *rsa, positionAndRotation *cfg,
+                             rectangle *clearances, rectangle *offlimits, vertex *vertices, vertex *surfaceRectangle,
+                             Surface *srf, gpuConfig *gpuCfg)
+{
+    static unsigned long long calls = 0;
+    mhOptions o;
+    default_options(&o);
+    const char *env = getenv("MH_SEED");
+    if (env && *env)
+        o.seed = strtoull(env, NULL, 0);
+    else /* Kernel.cu:943 seeds with time(NULL); the call counter keeps two calls in one second apart */
+        o.seed = (uint64_t)time(NULL) ^ ((uint64_t)__atomic_fetch_add(&calls, 1ULL, __ATOMIC_RELAXED) << 40);
+    return KernelWrapperEx(rss, rsa, cfg, clearances, offlimits, vertices, surfaceRectangle, srf, gpuCfg, &o);
+}
+
+MH_API void KernelFree(result *res)
+{
+    if (!res) return;
+    free(res[0].points);
+    free(res);
+}
+
+MH_API int KernelEvalCosts(const relationshipStruct *rss, const relationshipAngleStruct *rsa, const positionAndRotation *layouts,
+                           int nLayouts, const rectangle *clearances, const rectangle *offlimits, const vertex *vertices,
+                           const vertex *surfaceRectangle, const Surface *srf, resultCosts *out)
+{
+    g_err[0] = 0;
+    mhProblem P;
+    void *d_problem = NULL, *d_points = NULL, *d_costs = NULL, *stream = NULL;
+    point *pts = NULL;
+    int rc = -1;
+    if (nLayouts < 1 || !out || !layouts) { set_err("", "bad arguments", 0); return -1; }
+    if (pack_problem(rss, rsa, layouts, clearances, offlimits, vertices, surfaceRectangle, srf, &P)) return -1;
+    const int n = P.h->n;
+    const size_t cn = (size_t)nLayouts * (size_t)n;
+    pts = (point *)calloc(cn, sizeof(point));
+    if (!pts) { set_err("", "out of host memory", 0); goto fail; }
+    for (size_t i = 0; i < cn; i++) {
+        pts[i].x = (float)layouts[i].x; pts[i].y = (float)layouts[i].y; pts[i].rotY = (float)layouts[i].rotY;
+    }
+    const int lanes = choose_lanes(n, P.h->C, P.h->smem_words, nLayouts, 0);
+    if (lanes < 0) goto fail;
+    CU(mhdev_stream_create(&stream));
+    CU(mhdev_malloc(&d_problem, 4 * (size_t)P.h->total_words));
+    CU(mhdev_malloc(&d_points, sizeof(point) * cn));
+    CU(mhdev_malloc(&d_costs, sizeof(resultCosts) * (size_t)nLayouts));
+    CU(mhdev_h2d(d_problem, P.blob, 4 * (size_t)P.h->total_words, stream));
+    CU(mhdev_h2d(d_points, pts, sizeof(point) * cn, stream));
+    CU(mhdev_launch_score(d_problem, P.h->smem_words, n, P.h->C, P.h->R, nLayouts, lanes, d_points, d_costs, stream));
+    CU(mhdev_d2h(out, d_costs, sizeof(resultCosts) * (size_t)nLayouts, stream));
+    CU(mhdev_stream_sync(stream));
+    rc = 0;
+fail:
+    if (stream) mhdev_stream_sync(stream);
+    mhdev_free(d_problem); mhdev_free(d_points); mhdev_free(d_costs);
+    if (stream) mhdev_stream_destroy(stream);
+    free(pts);
+    free(P.blob);
+    return rc;
+}
+
+MH_API int KernelDeviceInfo(int *smCount, int *smClockKHz, int *ccMajor, int *ccMinor, char *name, int nameLen)
+{
+    g_err[0] = 0;
+    int e = mhdev_device_limits(NULL, NULL, smCount, smClockKHz, ccMajor, ccMinor, name, nameLen);
+    if (e) { set_err("%s failed: %s", "device query", e); return -1; }
+    return 0;
+}

@@ -1,0 +1,125 @@
+/*
+ * mh_abi.h -- the thin C ABI between the plain-C host code (kernel_wrapper.c) and the CUDA
+ * translation unit (mh_kernels.cu).  Launch descriptors and raw device-memory helpers only:
+ * no CUDA type crosses this line, so the host side compiles with a C compiler.
+ *
+ * Internal to libKernel.so (hidden visibility); the public ABI is include/mh_kernel.h.
+ */
+#ifndef MH_ABI_H
+#define MH_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Packed, single-precision problem description.  The host builds one blob: this header,
+ * then the arrays at the word offsets it names.  The first `smem_words` 4-byte words are
+ * staged into shared memory by every block; the tail (initial layout, pass-through fields)
+ * is read from global memory at chain start / write-out only.
+ *
+ * Every constant is derived from the caller's doubles in double precision and narrowed once,
+ * at the point where the reference narrows (see kernel_wrapper.c: pack_problem). */
+typedef struct mhProblemHeader {
+    int32_t n, C, R, any_free;
+    float w_focal, w_pair, w_visual, w_sym;
+    float w_off, w_clear, w_surf, denom;   /* denom = sum of length*width (Kernel.cu:199-202) */
+    float focal_x, focal_y, ux, uy;        /* (float)cos/sin(focalRot), Kernel.cu:290-291      */
+    float fdotu, two_focal_rot, cx2, cy2;  /* focal . u ; 2*focalRot ; centroid/2 (Q11)        */
+    float room_minx, room_miny, room_maxx, room_maxy; /* AABB of surfaceRectangle             */
+    float std_x, std_y, sigma_t, pi_cmp;   /* W/16, H/16 (Q19); 15/90*PI; largest float <= 3.1416 */
+    float two_pi, half_pi, two_pi_cmp, pad0; /* (float)6.2832, (float)1.5708, largest float <= 6.2832 */
+    int32_t off_obj_box;    /* float4[n] {min(v1x,v2x,v3x), min y, max x, max y} of the off-limit rect */
+    int32_t off_obj_v0x;    /* float[n]  x of its first vertex, never translated (quirk Q6)   */
+    int32_t off_obj_area;   /* float[n]  (float)(length*width)                                */
+    int32_t off_obj_frozen; /* int32[n]                                                        */
+    int32_t off_clr_box;    /* float4[C] same constants for the clearance rects               */
+    int32_t off_clr_v0x;    /* float[C]                                                        */
+    int32_t off_clr_src;    /* int32[C]  SourceIndex                                           */
+    int32_t off_rel_idx;    /* int4[R]   {rss Source, rss Target, rsa Source, rsa Target}      */
+    int32_t off_rel_rng;    /* float4[R] {1/start, end, angleMin, angleMax}                    */
+    int32_t off_rel_aux;    /* float4[R] {start, 1/norm, wraps (angleMin > angleMax), 0}       */
+    int32_t smem_words;     /* words [0, smem_words) go to shared memory                       */
+    int32_t off_cfg0;       /* float[3n] x, y, rotY of the caller's layout (global only)       */
+    int32_t off_pass;       /* float[3n] z, rotX, rotZ pass-through, narrowed (global only)    */
+    int32_t total_words;
+    int32_t pad1, pad2;
+} mhProblemHeader;
+
+enum { MH_SCHED_CONSTANT = 0, MH_SCHED_GEOMETRIC = 1, MH_SCHED_LINEAR = 2, MH_SCHED_PER_CHAIN = 3 };
+
+/* One launch of the chain kernel: advance `n_chains` chains by `it_count` iterations. */
+typedef struct mhLaunch {
+    const void *d_problem;
+    int32_t problem_words;  /* total words of the blob                                         */
+    int32_t smem_words;
+    int32_t n, C, R;
+    int32_t n_chains;       /* chains of this context (local)                                  */
+    int32_t lanes;          /* lanes per chain: 1,2,4,8,16,32                                  */
+    int32_t fresh;          /* 1: start from the problem's initial layout                      */
+    uint64_t seed;
+    uint64_t chain_offset;  /* global id of local chain i = chain_offset + i*chain_stride      */
+    uint64_t chain_stride;
+    uint64_t it_begin;
+    int32_t it_count;
+    int32_t schedule;       /* MH_SCHED_*                                                      */
+    int32_t schedule_length;
+    int32_t result_mode;    /* 0 final layout, 1 best layout                                   */
+    float beta_start;
+    float beta_end;
+    float beta_log2_ratio;  /* log2f(beta_end/beta_start)                                      */
+    float pad;
+    /* chain state, [chain][object] */
+    float *d_x, *d_y, *d_rot;
+    uint16_t *d_perm;       /* which original object's z/rotX/rotZ sits in slot i (swap moves)  */
+    float *d_cur_total;     /* [chain] totalCosts of the current layout                        */
+    float *d_best_total;    /* [chain]                                                         */
+    float *d_beta;          /* [chain] used when schedule == MH_SCHED_PER_CHAIN                */
+    void *d_points;         /* point[chain][object]                                            */
+    void *d_costs;          /* resultCosts[chain]                                              */
+    void *d_trace;          /* mhTraceEntry[it][chain] or NULL                                 */
+    void *stream;
+} mhLaunch;
+
+int mhdev_launch_chains(const mhLaunch *l);
+/* resultCosts of the layouts in d_points (all eight terms). */
+int mhdev_launch_score(const void *d_problem, int smem_words, int n, int C, int R, int n_layouts, int lanes,
+                       const void *d_points, void *d_costs, void *stream);
+/* Replica exchange between neighbouring rungs (extension).  all_total/all_beta hold the
+ * values of every chain of the ladders this context takes part in, indexed by global chain
+ * id - gather_base. */
+int mhdev_launch_exchange(int n_chains, uint64_t chain_offset, uint64_t chain_stride, int rungs, uint64_t epoch,
+                          uint64_t it_last, uint64_t seed, const float *d_all_total, const float *d_all_beta,
+                          uint64_t gather_base, float *d_beta, void *stream);
+/* arg-max of totalCosts over the context's chains: d_out = {float total, int32 chain}. */
+int mhdev_launch_argmax(const void *d_costs, int n_chains, void *d_out, void *stream);
+/* Largest dynamic shared memory per block and SM count / clock of the current device. */
+int mhdev_device_limits(int *max_smem_per_block, int *max_smem_per_sm, int *sm_count, int *clock_khz, int *cc_major,
+                        int *cc_minor, char *name, int name_len);
+int mhdev_chain_smem_bytes(int smem_words, int n, int C, int lanes, int warps_per_block);
+
+/* raw runtime helpers */
+int mhdev_get_device(int *dev);
+int mhdev_set_device(int dev);
+int mhdev_malloc(void **p, size_t bytes);
+void mhdev_free(void *p);
+int mhdev_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int mhdev_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int mhdev_memset(void *dst, int value, size_t bytes, void *stream);
+int mhdev_stream_create(void **stream);
+void mhdev_stream_destroy(void *stream);
+int mhdev_stream_sync(void *stream);
+int mhdev_event_create(void **ev);
+void mhdev_event_destroy(void *ev);
+int mhdev_event_record(void *ev, void *stream);
+int mhdev_event_elapsed_ms(void *e0, void *e1, float *ms); /* synchronises on e1 */
+int mhdev_host_alloc(void **p, size_t bytes);               /* pinned staging memory */
+void mhdev_host_free(void *p);
+const char *mhdev_error_string(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MH_ABI_H */

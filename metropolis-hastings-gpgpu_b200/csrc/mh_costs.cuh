@@ -1,0 +1,289 @@
+// mh_costs.cuh -- the Merrell et al. cost terms of the reference (Kernel.cu:162-550), written
+// for a group of G lanes that owns one layout ("chain").
+//
+// Data layout.  A warp holds CPW = 32/G chains.  Chain state (x, y, rotY per object) lives in
+// shared memory, interleaved by chain so that, for a fixed object j, the CPW chains of a warp
+// sit in consecutive banks:   X[j*CPW + c].   In the pair loops every lane of a group reads
+// the same word (a broadcast) and different groups read neighbouring words: conflict-free.
+// In the lane-strided O(n) loops lane (c, g) touches object g + G*k -> word (g+Gk)*CPW + c:
+// the 32 lanes of a warp cover 32 consecutive words: conflict-free.
+//
+// The O(n^2) and O(C n) terms are row-parallel: lane g owns rows i = g, g+G, ... and walks
+// all columns, keeping the running max / sum in registers; one xor-shuffle tree per term per
+// evaluation reduces over the group.
+//
+// Precision: float32 throughout (the reference mixes float and double per expression,
+// SURVEY.md section 8a); every quirk that changes VALUES is kept: PI = 3.1416 (Q4), the
+// off-limits term outside the total (Q5), the untranslated first vertex in the AABB min (Q6),
+// clearance i moved by object i in the surface term (Q7), translate-only rectangles (Q8), the
+// always-true angle condition (Q9), centroid/2 (Q11), one-sided angle wraps (Q18), the
+// distance x angle product (Q20).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mh_abi.h"
+
+namespace mh {
+
+struct SmemProblem {
+    const mhProblemHeader *h;
+    const float4 *obj_box;
+    const float *obj_v0x;
+    const float *obj_area;
+    const int *obj_frozen;
+    const float4 *clr_box;
+    const float *clr_v0x;
+    const int *clr_src;
+    const int4 *rel_idx;
+    const float4 *rel_rng;
+    const float4 *rel_aux;
+};
+
+__device__ __forceinline__ SmemProblem bind_problem(const float *base)
+{
+    SmemProblem P;
+    P.h = reinterpret_cast<const mhProblemHeader *>(base);
+    P.obj_box = reinterpret_cast<const float4 *>(base + P.h->off_obj_box);
+    P.obj_v0x = base + P.h->off_obj_v0x;
+    P.obj_area = base + P.h->off_obj_area;
+    P.obj_frozen = reinterpret_cast<const int *>(base + P.h->off_obj_frozen);
+    P.clr_box = reinterpret_cast<const float4 *>(base + P.h->off_clr_box);
+    P.clr_v0x = base + P.h->off_clr_v0x;
+    P.clr_src = reinterpret_cast<const int *>(base + P.h->off_clr_src);
+    P.rel_idx = reinterpret_cast<const int4 *>(base + P.h->off_rel_idx);
+    P.rel_rng = reinterpret_cast<const float4 *>(base + P.h->off_rel_rng);
+    P.rel_aux = reinterpret_cast<const float4 *>(base + P.h->off_rel_aux);
+    return P;
+}
+
+// Per-warp chain state in shared memory.
+template <int G> struct WarpState {
+    static constexpr int CPW = 32 / G;
+    float *X, *Y, *Rt;
+    float4 *CB;     // clearance AABBs of the layout under evaluation, [C][CPW]
+    uint16_t *perm; // [n][CPW]
+    __device__ __forceinline__ static int at(int j, int c) { return j * CPW + c; }
+    // words of shared memory one warp needs
+    __host__ __device__ static int words(int n, int C) { return (CPW * (3 * n + 4 * C) + (CPW * n + 1) / 2 + 3) & ~3; }
+    __device__ __forceinline__ void bind(float *base, int n, int C)
+    {
+        CB = reinterpret_cast<float4 *>(base); // keep the float4 array 16-byte aligned
+        X = base + 4 * C * CPW;
+        Y = X + n * CPW;
+        Rt = Y + n * CPW;
+        perm = reinterpret_cast<uint16_t *>(Rt + n * CPW);
+    }
+};
+
+// Sums are kept as POSITIVE magnitudes; the reference's "result -= ..." sign is applied once
+// in combine().
+struct RawTerms {
+    float pw;    // sum of pair-wise distance penalties        (Kernel.cu:210-233)
+    float pa;    // sum of pair-wise angle penalties           (Kernel.cu:236-263)
+    float vbx;   // sum area_i * x_i                           (Kernel.cu:197-203)
+    float vby;
+    float focal; // sum cos(phi_i)                             (Kernel.cu:266-281)
+    float sym;   // sum_i max(0, max_j ...)                    (Kernel.cu:283-318)
+    float clr;   // sum of clearance x off-limit overlaps      (Kernel.cu:404-434)
+    float surf;  // sum of areas outside the room              (Kernel.cu:437-483)
+    float off;   // sum of off-limit x off-limit overlaps      (Kernel.cu:485-514)
+};
+
+struct Costs8 {
+    float total, pair, visual, focal, sym, clr, off, surf; // field order of resultCosts
+};
+
+template <int G> __device__ __forceinline__ float group_sum(float v)
+{
+#pragma unroll
+    for (int m = G / 2; m > 0; m >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float pos(float v) { return fmaxf(v, 0.0f); }
+
+// AABB of a rectangle translated by (tx, ty): Kernel.cu:366-401 with the four-vertex min/max
+// hoisted (min(a+t, b+t) == min(a,b)+t in IEEE arithmetic).  Q6: the first vertex's x enters
+// the minimum untranslated.
+__device__ __forceinline__ float4 box_at(float4 k, float v0x, float tx, float ty)
+{
+    return make_float4(fminf(v0x, k.x + tx), k.y + ty, k.z + tx, k.w + ty);
+}
+
+// Kernel.cu:321-340: zero unless both extents are positive.
+__device__ __forceinline__ float overlap(float4 a, float4 b)
+{
+    const float w = fminf(a.z, b.z) - fmaxf(a.x, b.x);
+    const float h = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+    return pos(w) * pos(h);
+}
+
+// Area of box b outside the room: the four complement rectangles of Kernel.cu:343-364 with
+// +-DBL_MAX narrowed to +-inf by fmaxf/fminf (Kernel.cu:325-328), i.e. no clamp on that side.
+__device__ __forceinline__ float outside_room(float4 b, const mhProblemHeader *h)
+{
+    const float rx0 = h->room_minx, ry0 = h->room_miny, rx1 = h->room_maxx, ry1 = h->room_maxy;
+    const float w = pos(b.z - b.x);
+    const float hm = pos(fminf(b.w, ry1) - fmaxf(b.y, ry0));
+    float e = w * pos(fminf(b.w, ry0) - b.y);                 // below the room, all x
+    e = __fadd_rn(e, pos(fminf(b.z, rx0) - b.x) * hm);        // left of it
+    e = __fadd_rn(e, w * pos(b.w - fmaxf(b.y, ry1)));         // above
+    e = __fadd_rn(e, pos(b.z - fmaxf(b.x, rx1)) * hm);        // right
+    return e;
+}
+
+// All terms of one layout.  Every lane of the warp must call this (it synchronises the warp);
+// on return every lane of a group holds the group's totals.
+template <int G, bool WITH_OFFLIMITS>
+__device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState<G> &S, const int c, const int g, RawTerms &t)
+{
+    using WS = WarpState<G>;
+    const mhProblemHeader *h = P.h;
+    const int n = h->n, C = h->C, R = h->R;
+    float surf = 0.f, clr = 0.f, sym = 0.f, vbx = 0.f, vby = 0.f, focal = 0.f, off = 0.f, pw = 0.f, pa = 0.f;
+
+    // ---- clearance rectangles: at their source object for ClearanceCosts, at object k for
+    //      SurfaceAreaCosts (Q7) -------------------------------------------------------------
+    for (int k = g; k < C; k += G) {
+        const float4 kb = P.clr_box[k];
+        const float v0 = P.clr_v0x[k];
+        const int src = P.clr_src[k];
+        S.CB[WS::at(k, c)] = box_at(kb, v0, S.X[WS::at(src, c)], S.Y[WS::at(src, c)]);
+        surf += outside_room(box_at(kb, v0, S.X[WS::at(k, c)], S.Y[WS::at(k, c)]), h);
+    }
+    __syncwarp();
+
+    // ---- rows: one object per lane per pass ----------------------------------------------------
+    const float ux = h->ux, uy = h->uy, fdotu = h->fdotu, tfr = h->two_focal_rot;
+    const float pi_cmp = h->pi_cmp, two_pi = h->two_pi;
+    for (int i = g; i < n; i += G) {
+        const float xi = S.X[WS::at(i, c)], yi = S.Y[WS::at(i, c)], ri = S.Rt[WS::at(i, c)];
+        // visual balance partial sums (Kernel.cu:199-202)
+        const float area = P.obj_area[i];
+        vbx = fmaf(area, xi, vbx);
+        vby = fmaf(area, yi, vby);
+        // focal point: phi = atan2(fy - y, fx - x) - rot + PI/2 (Kernel.cu:185-188, 271-277)
+        {
+            const float ph = atan2f(h->focal_y - yi, h->focal_x - xi) - ri + h->half_pi;
+            focal += cosf(ph);
+        }
+        // own off-limit rectangle: outside the room, against every clearance
+        const float4 a = box_at(P.obj_box[i], P.obj_v0x[i], xi, yi);
+        surf += outside_room(a, h);
+        {
+            float acc = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < C; k++)
+                acc += overlap(a, S.CB[WS::at(k, c)]);
+            clr += acc;
+        }
+        // symmetry: reflect object i across the focal axis, best match over all j (Kernel.cu:290-314)
+        {
+            const float s = 2.0f * (fdotu - (xi * ux + yi * uy));
+            const float rx = xi + s * ux, ry = yi + s * uy;
+            float rr = tfr - ri;
+            if (rr < -pi_cmp) rr += two_pi;                    // Q18: one-sided wrap
+            float m = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < n; j++) {
+                const float dx = S.X[WS::at(j, c)] - rx, dy = S.Y[WS::at(j, c)] - ry;
+                const float sd = sqrt_approx(sqrt_approx(fmaf(dx, dx, dy * dy)));   // sqrt(Distance)
+                float dt = S.Rt[WS::at(j, c)] - rr;
+                dt = dt > pi_cmp ? dt - two_pi : dt;            // Q18
+                m = fmaxf(m, fmaf(-0.4f, fabsf(dt), 5.0f - sd));
+            }
+            sym += m;
+        }
+        if (WITH_OFFLIMITS) {                                   // Kernel.cu:488-511, pairs i < j
+            float acc = 0.f;
+            for (int j = i + 1; j < n; j++)
+                acc += overlap(a, box_at(P.obj_box[j], P.obj_v0x[j], S.X[WS::at(j, c)], S.Y[WS::at(j, c)]));
+            off += acc;
+        }
+    }
+
+    // ---- relationships --------------------------------------------------------------------------
+    for (int r = g; r < R; r += G) {
+        const int4 id = P.rel_idx[r];     // distance pair (x, y) from rss[r], angle pair (z, w) from rsa[r]
+        const float4 rg = P.rel_rng[r];   // 1/start, end, angleMin, angleMax
+        const float4 ax = P.rel_aux[r];   // start, 1/norm, wraps
+        {
+            const float dX = S.X[WS::at(id.x, c)] - S.X[WS::at(id.y, c)];
+            const float dY = S.Y[WS::at(id.x, c)] - S.Y[WS::at(id.y, c)];
+            const float d = sqrtf(fmaf(dX, dX, dY * dY));
+            if (d < ax.x) {                                     // too close (Kernel.cu:219-223)
+                const float f = d * rg.x;
+                pw = fmaf(f, f, pw);
+            } else if (d > rg.y) {                              // too far (Kernel.cu:225-229)
+                const float f = rg.y / d;
+                pw = fmaf(f, f, pw);
+            }
+        }
+        const float dX = S.X[WS::at(id.z, c)] - S.X[WS::at(id.w, c)];
+        const float dY = S.Y[WS::at(id.z, c)] - S.Y[WS::at(id.w, c)];
+        // bearing of source seen from target, relative to the target's rotation (Kernel.cu:170-182)
+        float tp = atan2f(dY, dX);
+        if (tp < 0.f) tp = two_pi + tp;
+        float th = tp - S.Rt[WS::at(id.w, c)];
+        if (th < 0.f) th = two_pi + th;
+        const float pen = fminf(fabsf(th - rg.z), fabsf(th - rg.w)) * ax.y;
+        if (ax.z != 0.f) {                                      // range crosses zero (Kernel.cu:245-250)
+            float f = rg.z + th;
+            if (f >= two_pi) {                                  // fmodf (Q17); one subtraction covers [0, 4 PI)
+                f -= two_pi;
+                if (f >= two_pi) f = fmodf(f, two_pi);
+            } else if (f < 0.f) {
+                f = fmodf(f, two_pi);
+            }
+            if (f > rg.w) pa += pen;
+        } else if (rg.z < th || th < rg.w) {                    // Q9: almost always true
+            pa += pen;
+        }
+    }
+
+    t.pw = group_sum<G>(pw);
+    t.pa = group_sum<G>(pa);
+    t.vbx = group_sum<G>(vbx);
+    t.vby = group_sum<G>(vby);
+    t.focal = group_sum<G>(focal);
+    t.sym = group_sum<G>(sym);
+    t.clr = group_sum<G>(clr);
+    t.surf = group_sum<G>(surf);
+    t.off = WITH_OFFLIMITS ? group_sum<G>(off) : 0.f;
+}
+
+// Costs() proper (Kernel.cu:516-550): each raw term is a float, weighted in float, and the
+// total is the left-to-right float sum of six of them (Q5).  __fmul_rn/__fadd_rn keep the
+// compiler from fusing a weight multiply into the running sum, which the reference cannot do
+// because it stores every weighted term first.
+__device__ __forceinline__ Costs8 combine(const mhProblemHeader *h, const RawTerms &t)
+{
+    Costs8 c;
+    c.pair = __fmul_rn(h->w_pair, __fmul_rn(t.pw, t.pa)); // (-pw)*(-pa): Q20
+    const float ax = t.vbx / h->denom, ay = t.vby / h->denom;
+    const float dX = ax - h->cx2, dY = ay - h->cy2;       // Q11
+    c.visual = __fmul_rn(h->w_visual, -sqrtf(fmaf(dX, dX, dY * dY)));
+    c.focal = __fmul_rn(h->w_focal, -t.focal);
+    c.sym = __fmul_rn(h->w_sym, -t.sym);
+    c.off = __fmul_rn(h->w_off, -t.off);
+    c.clr = __fmul_rn(h->w_clear, -t.clr);
+    c.surf = __fmul_rn(h->w_surf, -t.surf);
+    float tot = __fadd_rn(c.pair, c.visual);
+    tot = __fadd_rn(tot, c.focal);
+    tot = __fadd_rn(tot, c.sym);
+    tot = __fadd_rn(tot, c.clr);
+    tot = __fadd_rn(tot, c.surf);
+    c.total = tot;
+    return c;
+}
+
+} // namespace mh

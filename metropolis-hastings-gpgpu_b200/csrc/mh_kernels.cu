@@ -1,0 +1,497 @@
+// mh_kernels.cu -- sm_100a kernels of the Metropolis-Hastings layout optimiser and the
+// device half of the thin C ABI (mh_abi.h).
+//
+// mh_chain_kernel<G>   the hot path: one group of G lanes runs one chain (replaces the
+//                      reference's one-block-per-chain Kernel, Kernel.cu:754-871): in-register
+//                      Philox proposals, full cost re-evaluation from shared memory, the
+//                      exp(beta dE) accept test, optional best-layout tracking, coalesced
+//                      write-out.  No block-level barrier inside the iteration loop.
+// mh_score_kernel<G>   all eight cost terms of given layouts (fills resultCosts, which the
+//                      reference forgets -- quirk Q3; also the KernelEvalCosts parity hook).
+// mh_exchange_kernel   replica exchange between neighbouring temperature rungs (extension).
+// mh_argmax_kernel     best chain of a context.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "mh_abi.h"
+#include "mh_costs.cuh"
+#include "philox.cuh"
+
+namespace mh {
+
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr int THREADS = WARPS_PER_BLOCK * 32;
+
+struct PointRec {
+    float x, y, z, rotX, rotY, rotZ;
+};
+struct TraceRec {
+    int32_t move, obj1, obj2, accepted;
+    float star_total, cur_total, u, beta;
+};
+
+__device__ __forceinline__ void stage_problem(float *smem, const float *g, int words)
+{
+    // words is a multiple of 4 and both sides are 16-byte aligned
+    const float4 *src = reinterpret_cast<const float4 *>(g);
+    float4 *dst = reinterpret_cast<float4 *>(smem);
+    for (int i = threadIdx.x; i < words / 4; i += blockDim.x)
+        dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+// Write one chain's layout as point records: every lane of the warp takes part and the 6n
+// floats of the chain leave as consecutive 8-byte stores (256 B per warp instruction).
+template <int G>
+__device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc, int n, const float *pass, PointRec *out, int lane)
+{
+    using WS = WarpState<G>;
+    float2 *o2 = reinterpret_cast<float2 *>(out);
+    for (int q = lane; q < 3 * n; q += 32) {
+        const int i = q / 3, part = q - 3 * i;
+        const int src = S.perm[WS::at(i, cc)];
+        float2 v;
+        if (part == 0) v = make_float2(S.X[WS::at(i, cc)], S.Y[WS::at(i, cc)]);
+        else if (part == 1) v = make_float2(pass[src], pass[n + src]);           // z, rotX travel with swaps
+        else v = make_float2(S.Rt[WS::at(i, cc)], pass[2 * n + src]);            // rotY, rotZ
+        o2[q] = v;
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(THREADS) mh_chain_kernel(const mhLaunch L)
+{
+    using WS = WarpState<G>;
+    constexpr int CPW = WS::CPW;
+    extern __shared__ __align__(16) float smem[];
+    const float *gprob = static_cast<const float *>(L.d_problem);
+    stage_problem(smem, gprob, L.smem_words);
+    const SmemProblem P = bind_problem(smem);
+    const mhProblemHeader *h = P.h;
+    const int n = h->n, C = h->C;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = lane / G, g = lane % G;
+    WS S;
+    S.bind(smem + L.smem_words + warp * WS::words(n, C), n, C);
+
+    const int chain_raw = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + c;
+    const bool live = chain_raw < L.n_chains;
+    const int chain = live ? chain_raw : L.n_chains - 1;   // idle groups shadow the last chain, write nothing
+    const uint64_t gchain = L.chain_offset + (uint64_t)chain * L.chain_stride;
+    const float *cfg0 = gprob + h->off_cfg0;
+    const float *pass = gprob + h->off_pass;
+    PointRec *points = static_cast<PointRec *>(L.d_points);
+
+    // ---- load chain state -----------------------------------------------------------------------
+    for (int i = g; i < n; i += G) {
+        if (L.fresh) {
+            S.X[WS::at(i, c)] = cfg0[i];
+            S.Y[WS::at(i, c)] = cfg0[n + i];
+            S.Rt[WS::at(i, c)] = cfg0[2 * n + i];
+            S.perm[WS::at(i, c)] = (uint16_t)i;
+        } else {
+            const size_t o = (size_t)chain * n + i;
+            S.X[WS::at(i, c)] = L.d_x[o];
+            S.Y[WS::at(i, c)] = L.d_y[o];
+            S.Rt[WS::at(i, c)] = L.d_rot[o];
+            S.perm[WS::at(i, c)] = L.d_perm[o];
+        }
+    }
+    __syncwarp();
+
+    float cur, best;
+    if (L.fresh) {
+        RawTerms t;
+        eval_terms<G, false>(P, S, c, g, t);
+        cur = combine(h, t).total;                            // Kernel.cu:778
+        best = cur;
+        if (L.result_mode == 1) {
+            __syncwarp();
+            for (int cc = 0; cc < CPW; cc++) {
+                const int ch = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + cc;
+                if (ch < L.n_chains) write_points_warp<G>(S, cc, n, pass, points + (size_t)ch * n, lane);
+            }
+        }
+    } else {
+        cur = L.d_cur_total[chain];
+        best = L.d_best_total[chain];
+    }
+
+    const float room_x0 = h->room_minx, room_y0 = h->room_miny, room_x1 = h->room_maxx, room_y1 = h->room_maxy;
+    const int any_free = h->any_free;
+    TraceRec *trace = static_cast<TraceRec *>(L.d_trace);
+    float beta = L.beta_start;
+    if (L.schedule == MH_SCHED_PER_CHAIN) beta = L.d_beta[chain];
+
+    // ---- the chain (Kernel.cu:785-827, Semantics S of SURVEY.md section 8a) ---------------------
+    for (int k = 0; k < L.it_count; k++) {
+        const uint64_t it = L.it_begin + (uint64_t)k;
+        if (L.schedule == MH_SCHED_GEOMETRIC || L.schedule == MH_SCHED_LINEAR) {
+            const int len = L.schedule_length;
+            const uint64_t ic = it < (uint64_t)(len - 1) ? it : (uint64_t)(len - 1);
+            const float tt = len > 1 ? (float)((double)ic / (double)(len - 1)) : 0.f;
+            beta = L.schedule == MH_SCHED_GEOMETRIC ? L.beta_start * exp2f(tt * L.beta_log2_ratio)
+                                                    : L.beta_start + (L.beta_end - L.beta_start) * tt;
+        }
+
+        // -- propose (Kernel.cu:576-704): every lane of the group derives the same move -------------
+        const Philox4 w = draw_block(L.seed, gchain, it, 0);
+        const int p = random_int(uniform01(w.x), 2);
+        int a = -1, b = -1;
+        float ax = 0.f, ay = 0.f, ar = 0.f, bx = 0.f, by = 0.f, br = 0.f;        // proposed values
+        float oax = 0.f, oay = 0.f, oar = 0.f, obx = 0.f, oby = 0.f, obr = 0.f;  // values to restore
+        if (any_free && (p != 2 || n >= 2)) {
+            uint32_t redraw = 2;
+            a = random_int(uniform01(w.y), n - 1);
+            if (p == 2) b = random_int(uniform01(w.z), n - 1);
+            while (P.obj_frozen[a] || (b >= 0 && P.obj_frozen[b])) {            // Kernel.cu:601, 637, 662, 666
+                const Philox4 rw = draw_block(L.seed, gchain, it, redraw++);
+                if (P.obj_frozen[a]) a = random_int(uniform01(rw.x), n - 1);
+                if (b >= 0 && P.obj_frozen[b]) b = random_int(uniform01(rw.y), n - 1);
+            }
+            oax = S.X[WS::at(a, c)];
+            oay = S.Y[WS::at(a, c)];
+            oar = S.Rt[WS::at(a, c)];
+            ax = oax; ay = oay; ar = oar;
+            if (p == 0) {                                      // translate, sigma = W/16, H/16 (Q19), snap to the room
+                float n0, n1;
+                box_muller(w.z, w.w, n0, n1);
+                const float nx = oax + n0 * h->std_x, ny = oay + n1 * h->std_y;
+                ax = nx > room_x1 ? room_x1 : (nx < room_x0 ? room_x0 : nx);
+                ay = ny > room_y1 ? room_y1 : (ny < room_y0 ? room_y0 : ny);
+            } else if (p == 1) {                               // rotate, one wrap into [0, 2 PI] (Kernel.cu:645-651)
+                float n0, n1;
+                box_muller(w.z, w.w, n0, n1);
+                ar = oar + n0 * h->sigma_t;
+                if (ar < 0.f) ar += h->two_pi;
+                else if (ar > h->two_pi_cmp) ar -= h->two_pi;
+            } else {                                           // swap position and rotation (Kernel.cu:675-700)
+                obx = S.X[WS::at(b, c)];
+                oby = S.Y[WS::at(b, c)];
+                obr = S.Rt[WS::at(b, c)];
+                ax = obx; ay = oby; ar = obr;
+                bx = oax; by = oay; br = oar;
+            }
+        }
+        __syncwarp();
+        if (g == 0 && a >= 0) {
+            S.X[WS::at(a, c)] = ax; S.Y[WS::at(a, c)] = ay; S.Rt[WS::at(a, c)] = ar;
+            if (b >= 0) { S.X[WS::at(b, c)] = bx; S.Y[WS::at(b, c)] = by; S.Rt[WS::at(b, c)] = br; }
+        }
+        __syncwarp();
+
+        // -- evaluate the proposal (Kernel.cu:804): every live term, from scratch -----------------
+        RawTerms t;
+        eval_terms<G, false>(P, S, c, g, t);
+        const float star = combine(h, t).total;
+
+        // -- accept (Kernel.cu:706-713): u < min(1, exp(beta (star - cur))), maximises (Q10) ------
+        const float u = uniform01(draw_block(L.seed, gchain, it, 1).x);
+        const bool acc = u < fminf(1.0f, (float)exp((double)beta * ((double)star - (double)cur)));
+        __syncwarp();
+        if (acc) {
+            cur = star;
+            if (g == 0 && b >= 0) {
+                const uint16_t pa = S.perm[WS::at(a, c)];
+                S.perm[WS::at(a, c)] = S.perm[WS::at(b, c)];
+                S.perm[WS::at(b, c)] = pa;
+            }
+        } else if (g == 0 && a >= 0) {
+            S.X[WS::at(a, c)] = oax; S.Y[WS::at(a, c)] = oay; S.Rt[WS::at(a, c)] = oar;
+            if (b >= 0) { S.X[WS::at(b, c)] = obx; S.Y[WS::at(b, c)] = oby; S.Rt[WS::at(b, c)] = obr; }
+        }
+        __syncwarp();
+        if (L.result_mode == 1) {
+            // best layout so far = highest totalCosts; it can only improve on an accepted move
+            const bool improved = acc && cur > best;
+            if (improved) best = cur;
+            const unsigned mask = __ballot_sync(0xffffffffu, improved && live);
+            if (mask) {
+                for (int cc = 0; cc < CPW; cc++)
+                    if (mask & (1u << (cc * G))) {
+                        const int ch = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + cc;
+                        write_points_warp<G>(S, cc, n, pass, points + (size_t)ch * n, lane);
+                    }
+            }
+        }
+        if (trace && live && g == 0) {
+            TraceRec r;
+            r.move = p; r.obj1 = a; r.obj2 = b; r.accepted = acc ? 1 : 0;
+            r.star_total = star; r.cur_total = cur; r.u = u; r.beta = beta;
+            trace[(size_t)k * L.n_chains + chain] = r;
+        }
+    }
+
+    // ---- persist the chain, emit the result ------------------------------------------------------
+    __syncwarp();
+    if (live) {
+        for (int i = g; i < n; i += G) {
+            const size_t o = (size_t)chain * n + i;
+            L.d_x[o] = S.X[WS::at(i, c)];
+            L.d_y[o] = S.Y[WS::at(i, c)];
+            L.d_rot[o] = S.Rt[WS::at(i, c)];
+            L.d_perm[o] = S.perm[WS::at(i, c)];
+        }
+        if (g == 0) {
+            L.d_cur_total[chain] = cur;
+            L.d_best_total[chain] = best;
+        }
+    }
+    if (L.result_mode == 0) {                                  // Kernel.cu:834-842: the final current layout
+        for (int cc = 0; cc < CPW; cc++) {
+            const int ch = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + cc;
+            if (ch < L.n_chains) write_points_warp<G>(S, cc, n, pass, points + (size_t)ch * n, lane);
+        }
+    }
+}
+
+// resultCosts of given layouts: loads x, y, rotY from point records and evaluates all eight terms.
+template <int G>
+__global__ void __launch_bounds__(THREADS) mh_score_kernel(const float *__restrict__ gprob, int smem_words, int n_layouts,
+                                                           const PointRec *__restrict__ points, Costs8 *__restrict__ costs)
+{
+    using WS = WarpState<G>;
+    constexpr int CPW = WS::CPW;
+    extern __shared__ __align__(16) float smem[];
+    stage_problem(smem, gprob, smem_words);
+    const SmemProblem P = bind_problem(smem);
+    const int n = P.h->n, C = P.h->C;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = lane / G, g = lane % G;
+    WS S;
+    S.bind(smem + smem_words + warp * WS::words(n, C), n, C);
+    const int raw = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + c;
+    const bool live = raw < n_layouts;
+    const int l = live ? raw : n_layouts - 1;
+    for (int i = g; i < n; i += G) {
+        const PointRec pr = points[(size_t)l * n + i];
+        S.X[WS::at(i, c)] = pr.x;
+        S.Y[WS::at(i, c)] = pr.y;
+        S.Rt[WS::at(i, c)] = pr.rotY;
+    }
+    __syncwarp();
+    RawTerms t;
+    eval_terms<G, true>(P, S, c, g, t);
+    const Costs8 r = combine(P.h, t);
+    if (live && g == 0) costs[l] = r;
+}
+
+// Replica exchange (extension; the reference has a single fixed BETA).  One thread per local
+// chain.  Pairs (r, r+1) with r = epoch parity, r+1 < rungs; both members evaluate the same
+// decision from the gathered totals/betas, so no communication beyond the gather is needed.
+__global__ void mh_exchange_kernel(int n_chains, uint64_t chain_offset, uint64_t chain_stride, int rungs, uint64_t epoch,
+                                   uint64_t it_last, uint64_t seed, const float *__restrict__ all_total,
+                                   const float *__restrict__ all_beta, uint64_t gather_base, float *__restrict__ beta)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chains) return;
+    const uint64_t gch = chain_offset + (uint64_t)i * chain_stride;
+    const int r = (int)(gch % (uint64_t)rungs);
+    const int par = (int)(epoch & 1);
+    int lo_r;
+    if (((r - par) & 1) == 0 && r >= par) lo_r = r;     // this chain is the lower member of its pair
+    else lo_r = r - 1;
+    if (lo_r < par || lo_r + 1 >= rungs) return;
+    const uint64_t glo = gch - (uint64_t)(r - lo_r), ghi = glo + 1;
+    const float u = uniform01(draw_block(seed, glo, it_last, 0xFFFFu).x);
+    const double Ea = -(double)all_total[glo - gather_base], Eb = -(double)all_total[ghi - gather_base];
+    const double ba = (double)all_beta[glo - gather_base], bb = (double)all_beta[ghi - gather_base];
+    const float pacc = fminf(1.0f, (float)exp((ba - bb) * (Ea - Eb)));
+    if (u < pacc) beta[i] = (float)(r == lo_r ? bb : ba);
+}
+
+__global__ void mh_argmax_kernel(const Costs8 *__restrict__ costs, int n, float *out_total, int *out_idx)
+{
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    float bv = -INFINITY;
+    int bi = -1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = costs[i].total;
+        if (v > bv || bi < 0) { bv = v; bi = i; }
+    }
+    for (int m = 16; m > 0; m >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, m);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+        if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) / 32;
+        bv = threadIdx.x < nw ? sv[threadIdx.x] : -INFINITY;
+        bi = threadIdx.x < nw ? si[threadIdx.x] : -1;
+        for (int m = 16; m > 0; m >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, m);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+            if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) { *out_total = bv; *out_idx = bi; }
+    }
+}
+
+template <int G> static int launch_chains_g(const mhLaunch &L)
+{
+    using WS = WarpState<G>;
+    const int chains_per_block = WARPS_PER_BLOCK * WS::CPW;
+    const int blocks = (L.n_chains + chains_per_block - 1) / chains_per_block;
+    const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)WARPS_PER_BLOCK * WS::words(L.n, L.C));
+    cudaError_t e = cudaFuncSetAttribute(mh_chain_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    mh_chain_kernel<G><<<blocks, THREADS, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
+    return (int)cudaGetLastError();
+}
+
+template <int G>
+static int launch_score_g(const void *d_problem, int smem_words, int n, int C, int n_layouts, const void *d_points, void *d_costs,
+                          void *stream)
+{
+    using WS = WarpState<G>;
+    const int per_block = WARPS_PER_BLOCK * WS::CPW;
+    const int blocks = (n_layouts + per_block - 1) / per_block;
+    const size_t smem = sizeof(float) * ((size_t)smem_words + (size_t)WARPS_PER_BLOCK * WS::words(n, C));
+    cudaError_t e = cudaFuncSetAttribute(mh_score_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    mh_score_kernel<G><<<blocks, THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float *>(d_problem), smem_words, n_layouts, static_cast<const PointRec *>(d_points),
+        static_cast<Costs8 *>(d_costs));
+    return (int)cudaGetLastError();
+}
+
+} // namespace mh
+
+extern "C" {
+
+int mhdev_chain_smem_bytes(int smem_words, int n, int C, int lanes, int warps_per_block)
+{
+    int w = 0;
+    switch (lanes) {
+    case 1: w = mh::WarpState<1>::words(n, C); break;
+    case 2: w = mh::WarpState<2>::words(n, C); break;
+    case 4: w = mh::WarpState<4>::words(n, C); break;
+    case 8: w = mh::WarpState<8>::words(n, C); break;
+    case 16: w = mh::WarpState<16>::words(n, C); break;
+    case 32: w = mh::WarpState<32>::words(n, C); break;
+    default: return -1;
+    }
+    if (warps_per_block <= 0) warps_per_block = mh::WARPS_PER_BLOCK;
+    return 4 * (smem_words + warps_per_block * w);
+}
+
+int mhdev_launch_chains(const mhLaunch *l)
+{
+    if (l->n_chains <= 0) return 0;
+    switch (l->lanes) {
+    case 1: return mh::launch_chains_g<1>(*l);
+    case 2: return mh::launch_chains_g<2>(*l);
+    case 4: return mh::launch_chains_g<4>(*l);
+    case 8: return mh::launch_chains_g<8>(*l);
+    case 16: return mh::launch_chains_g<16>(*l);
+    case 32: return mh::launch_chains_g<32>(*l);
+    }
+    return (int)cudaErrorInvalidValue;
+}
+
+int mhdev_launch_score(const void *d_problem, int smem_words, int n, int C, int R, int n_layouts, int lanes, const void *d_points,
+                       void *d_costs, void *stream)
+{
+    (void)R;
+    if (n_layouts <= 0) return 0;
+    switch (lanes) {
+    case 1: return mh::launch_score_g<1>(d_problem, smem_words, n, C, n_layouts, d_points, d_costs, stream);
+    case 2: return mh::launch_score_g<2>(d_problem, smem_words, n, C, n_layouts, d_points, d_costs, stream);
+    case 4: return mh::launch_score_g<4>(d_problem, smem_words, n, C, n_layouts, d_points, d_costs, stream);
+    case 8: return mh::launch_score_g<8>(d_problem, smem_words, n, C, n_layouts, d_points, d_costs, stream);
+    case 16: return mh::launch_score_g<16>(d_problem, smem_words, n, C, n_layouts, d_points, d_costs, stream);
+    case 32: return mh::launch_score_g<32>(d_problem, smem_words, n, C, n_layouts, d_points, d_costs, stream);
+    }
+    return (int)cudaErrorInvalidValue;
+}
+
+int mhdev_launch_exchange(int n_chains, uint64_t chain_offset, uint64_t chain_stride, int rungs, uint64_t epoch, uint64_t it_last,
+                          uint64_t seed, const float *d_all_total, const float *d_all_beta, uint64_t gather_base, float *d_beta,
+                          void *stream)
+{
+    if (n_chains <= 0) return 0;
+    mh::mh_exchange_kernel<<<(n_chains + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        n_chains, chain_offset, chain_stride, rungs, epoch, it_last, seed, d_all_total, d_all_beta, gather_base, d_beta);
+    return (int)cudaGetLastError();
+}
+
+int mhdev_launch_argmax(const void *d_costs, int n_chains, void *d_out, void *stream)
+{
+    mh::mh_argmax_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const mh::Costs8 *>(d_costs), n_chains,
+                                                                           static_cast<float *>(d_out),
+                                                                           reinterpret_cast<int *>(static_cast<float *>(d_out) + 1));
+    return (int)cudaGetLastError();
+}
+
+int mhdev_device_limits(int *max_smem_per_block, int *max_smem_per_sm, int *sm_count, int *clock_khz, int *cc_major, int *cc_minor,
+                        char *name, int name_len)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    int v = 0;
+    if (max_smem_per_block) { e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); if (e) return (int)e; *max_smem_per_block = v; }
+    if (max_smem_per_sm) { e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev); if (e) return (int)e; *max_smem_per_sm = v; }
+    if (sm_count) { e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); if (e) return (int)e; *sm_count = v; }
+    if (clock_khz) { e = cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, dev); if (e) return (int)e; *clock_khz = v; }
+    if (cc_major) { e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev); if (e) return (int)e; *cc_major = v; }
+    if (cc_minor) { e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev); if (e) return (int)e; *cc_minor = v; }
+    if (name && name_len > 0) {
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, dev);
+        if (e) return (int)e;
+        snprintf(name, (size_t)name_len, "%s", prop.name);
+    }
+    return 0;
+}
+
+int mhdev_get_device(int *dev) { return (int)cudaGetDevice(dev); }
+int mhdev_set_device(int dev) { return (int)cudaSetDevice(dev); }
+int mhdev_malloc(void **p, size_t bytes) { return (int)cudaMalloc(p, bytes ? bytes : 16); }
+void mhdev_free(void *p) { if (p) cudaFree(p); }
+int mhdev_h2d(void *dst, const void *src, size_t bytes, void *stream)
+{
+    return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
+}
+int mhdev_d2h(void *dst, const void *src, size_t bytes, void *stream)
+{
+    return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream));
+}
+int mhdev_memset(void *dst, int value, size_t bytes, void *stream)
+{
+    return (int)cudaMemsetAsync(dst, value, bytes, static_cast<cudaStream_t>(stream));
+}
+int mhdev_stream_create(void **stream)
+{
+    cudaStream_t s;
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    *stream = e == cudaSuccess ? static_cast<void *>(s) : nullptr;
+    return (int)e;
+}
+void mhdev_stream_destroy(void *stream) { if (stream) cudaStreamDestroy(static_cast<cudaStream_t>(stream)); }
+int mhdev_stream_sync(void *stream) { return (int)cudaStreamSynchronize(static_cast<cudaStream_t>(stream)); }
+int mhdev_event_create(void **ev)
+{
+    cudaEvent_t e;
+    cudaError_t r = cudaEventCreate(&e);
+    *ev = r == cudaSuccess ? static_cast<void *>(e) : nullptr;
+    return (int)r;
+}
+void mhdev_event_destroy(void *ev) { if (ev) cudaEventDestroy(static_cast<cudaEvent_t>(ev)); }
+int mhdev_event_record(void *ev, void *stream) { return (int)cudaEventRecord(static_cast<cudaEvent_t>(ev), static_cast<cudaStream_t>(stream)); }
+int mhdev_event_elapsed_ms(void *e0, void *e1, float *ms)
+{
+    cudaError_t r = cudaEventSynchronize(static_cast<cudaEvent_t>(e1));
+    if (r != cudaSuccess) return (int)r;
+    return (int)cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(e0), static_cast<cudaEvent_t>(e1));
+}
+int mhdev_host_alloc(void **p, size_t bytes) { return (int)cudaMallocHost(p, bytes ? bytes : 16); }
+void mhdev_host_free(void *p) { if (p) cudaFreeHost(p); }
+const char *mhdev_error_string(int code) { return cudaGetErrorString(static_cast<cudaError_t>(code)); }
+
+} // extern "C"

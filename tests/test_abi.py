@@ -1,0 +1,91 @@
+"""CPU tests of the drop-in boundary: the library loads, exports every symbol that
+include/mh_kernel.h declares, the headers compile as C and C++, the numpy mirrors agree with
+the C layout, and -- without a GPU -- the compute entry points fail loudly instead of falling
+back to anything."""
+import ctypes as C
+import importlib
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pkg = importlib.import_module("metropolis-hastings-gpgpu_b200")
+L, S = pkg.layout, pkg.synth
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_numpy_mirrors_match_header_sizes():
+    assert L.check_layout()
+    assert L.mhOptions.itemsize == 80 and L.mhTraceEntry.itemsize == 32
+
+
+def test_headers_compile_as_c_and_cpp(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "mh_kernel.h"\nint main(void){return (int)sizeof(mhOptions) - 80;}\n')
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++11")):
+        exe = tmp_path / ("t_" + cc)
+        subprocess.run([cc, std, "-x", "c" if cc == "gcc" else "c++", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                       check=True)
+        assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_library_exports_every_declared_symbol():
+    path = pkg.lib_path()
+    assert os.path.exists(path), "libKernel.so not built: run __graft_entry__.build()"
+    hdr = open(os.path.join(ROOT, "include", "mh_kernel.h")).read()
+    declared = set(re.findall(r"MH_API\s+[\w\s\*]+?\b(Kernel\w+)\s*\(", hdr))
+    assert "KernelWrapper" in declared and len(declared) >= 16
+    assert declared == set(pkg.binding.EXPORTS)
+    lib = C.CDLL(path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert exported == declared, exported ^ declared        # nothing else leaks out of the library
+
+
+def test_oracle_is_not_linked_into_the_product():
+    out = subprocess.run(["nm", "-D", pkg.lib_path()], capture_output=True, text=True, check=True).stdout
+    assert "oracle" not in out
+    for f in os.listdir(os.path.join(ROOT, "metropolis-hastings-gpgpu_b200", "csrc")):
+        if f.endswith((".c", ".cu", ".cuh", ".h")):
+            assert "oracle" not in open(os.path.join(ROOT, "metropolis-hastings-gpgpu_b200", "csrc", f)).read().replace("test oracle", ""), f
+
+
+def test_bad_arguments_are_rejected_before_any_device_work():
+    k = pkg.Kernel()
+    room = S.make_config(1)
+    room.srf["nClearances"] = room.n + 1                       # quirk Q7 needs C <= n
+    with pytest.raises(pkg.KernelError, match="nClearances"):
+        k.wrapper_ex(room, 1, 1, seed=1)
+    room = S.make_config(1)
+    room.offlimits["point1Index"][0] = 10 ** 6
+    with pytest.raises(pkg.KernelError, match="point1Index"):
+        k.wrapper_ex(room, 1, 1, seed=1)
+    room = S.make_config(1)
+    room.rss["TargetIndex"][0] = -1
+    with pytest.raises(pkg.KernelError, match="relationship"):
+        k.wrapper_ex(room, 1, 1, seed=1)
+    with pytest.raises(pkg.KernelError, match="gridxDim"):
+        k.wrapper_ex(S.make_config(1), 0, 1, seed=1)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_gpu_means_loud_failure_not_a_cpu_fallback():
+    k = pkg.Kernel()
+    room = S.make_config(1)
+    with pytest.raises(pkg.KernelError) as e:
+        k.wrapper(room, 2, 10)
+    assert "failed" in str(e.value)
+    with pytest.raises(pkg.KernelError):
+        k.eval_costs(room, room.cfg)
