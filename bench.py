@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- MH proposals evaluated per second (chains x iterations / s), BASELINE.json's
+headline metric, on the 50-object living room (config 3: n=50, C=25, R=50, 65536 chains x
+10000 iterations, all cost terms, beta = 2).
+
+  python bench.py --gpus N --steps K --warmup W            this repo's sm_100a path
+  python bench.py --impl reference ...                      the reference's own kernel, rebuilt for
+                                                            sm_100 from /root/reference (oracle/_ref)
+
+One step = one pass of the hot path over the whole batch: every chain runs `iterations` MH steps
+from the caller's layout.  `value` is timed with the problem and chain state already resident in
+HBM (KernelCreate once, then KernelReset + KernelRun per step, CUDA events around the kernel);
+`e2e` is the same job through the reference-facing call KernelWrapperEx with host buffers (H2D of
+the room, the kernels, D2H of every layout and its costs, result assembly).  Prints ONE JSON line.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "MH proposals evaluated/sec (chains x iters/s) at 50 objects"
+UNIT = "proposals/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            busy = [s for s, w in zip(sm, power) if w >= 0.5 * max(power)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power))
+        return out
+
+
+def cpu_baseline(room, target_seconds=12.0):
+    """The oracle's C transcription of the per-chain loop (oracle/mh_oracle.c), one chain per
+    OpenMP thread on all host cores, on a bounded sample of the same workload."""
+    from oracle_lib import Oracle
+    o = Oracle()
+    threads = int(o.lib.oracle_max_threads())
+    chains = threads * 4
+    _, _, secs, th = o.run(room, chains, 20, seed=1, timed=True)          # calibrate
+    rate = chains * 20 / max(secs, 1e-6)
+    iters = max(20, int(rate * target_seconds / chains))
+    _, _, secs, th = o.run(room, chains, iters, seed=1, timed=True)
+    return {"value": chains * iters / secs, "unit": UNIT, "cores": th, "kind": "port",
+            "sample": f"{chains} chains x {iters} iterations of the same room ({secs:.1f} s), gcc -O2, OpenMP"}
+
+
+def reference_gpu(config_id, chains, iters, steps, warmup, timeout_s=300):
+    """The reference's own KernelWrapper rebuilt for sm_100 (oracle/_ref/libKernel_ref_nb.so: the
+    unmodified Kernel.cu with the one divergent barrier that deadlocks on sm_70+ neutralised, see
+    oracle/ref_gpu_harness.cu), at the launch shape its main() uses (blockxDim = 64).  Runs in a
+    subprocess under a timeout: a hang of the reference must not take the bench down.
+    Returns (proposals/s over the whole call, proposals/s by device events, seconds per step)."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), "nb", str(config_id), str(chains), str(iters), "64",
+           str(warmup), str(steps)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+    if out.returncode != 0:
+        raise RuntimeError("reference kernel failed: " + (out.stderr.strip().splitlines() or ["?"])[-1])
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    return r["proposals_per_s"], chains * iters / r["dev_s"], r["wall_s"]
+
+
+def run_reference_arm(args, room, rank):
+    if rank != 0:
+        return
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 mixed", "data": "synthetic"}
+    chains, iters = args.ref_chains, args.ref_iterations
+    try:
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libKernel_ref_nb.so")):
+            raise RuntimeError("oracle/_ref/libKernel_ref_nb.so not built")
+        v_wall, v_dev, step_s = reference_gpu(args.config, chains, iters, args.steps, args.warmup)
+        line.update(value=v_wall, ms_per_step=step_s * 1e3,
+                    config={"workload": f"config 3 living room n=50 C=25 R=50, bounded sample {chains} chains x {iters} iterations per step",
+                            "implementation": "reference Kernel.cu:873 KernelWrapper rebuilt for sm_100 (blockxDim=64; its one divergent __syncthreads, which deadlocks on sm_70+, neutralised), whole call incl. its H2D/D2H and curand init"},
+                    cpu_baseline={"value": v_wall, "unit": UNIT, "cores": 0, "kind": "reference",
+                                  "sample": f"{chains} chains x {iters} iterations; the reference's path is a CUDA kernel, timed on the same B200 (device-event rate {v_dev:.4g}/s)"},
+                    e2e={"value": v_wall, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
+    except Exception as ex:  # no GPU build of the reference: its algorithm as transcribed C on the host cores
+        cb = cpu_baseline(room, target_seconds=max(5.0, 4.0 * args.steps))
+        cb["sample"] += f" (reference kernel unavailable: {ex})"
+        line.update(value=cb["value"], ms_per_step=None, config={"workload": "config 3 living room n=50 C=25 R=50, bounded sample", "implementation": "oracle port on host cores"},
+                    cpu_baseline=cb, e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=3)
+    ap.add_argument("--chains", type=int, default=65536, help="chains per GPU (weak scaling)")
+    ap.add_argument("--iterations", type=int, default=10000)
+    ap.add_argument("--ref-chains", type=int, default=4096)
+    ap.add_argument("--ref-iterations", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    pkg = importlib.import_module("metropolis-hastings-gpgpu_b200")
+    room = pkg.synth.make_config(args.config)
+
+    if args.impl == "reference":
+        run_reference_arm(args, room, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    k = pkg.Kernel()
+    info = k.device_info()
+    n = room.n
+    total_chains = args.chains * world
+    offset = rank * args.chains
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = k.create(room, args.chains, seed=20261018, chain_offset=offset, lanes_per_chain=args.lanes)
+    ctx.set_stream(stream)
+
+    def step():
+        flush.zero_()
+        ctx.reset()
+        ctx.run(args.iterations)
+        return pkg.dist.global_best(k, ctx, n, offset, total_chains, rank, world, device, dist if world > 1 else None)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.stats()
+    ms0, l0 = ctx.stats()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t0 = time.perf_counter()
+    best = None
+    for _ in range(args.steps):
+        best = step()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms1, l1 = ctx.stats()
+    clocks = sampler.stop() if sampler else None
+    kernel_s = (ms1 - ms0) * 1e-3                       # CUDA events around the chain kernels only
+    t = torch.tensor([wall, kernel_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_max, kernel_max = float(t[0]), float(t[1])
+    proposals = float(total_chains) * args.iterations * args.steps
+    value = proposals / wall_max
+
+    # ---- e2e: the reference-facing call with HOST buffers --------------------------------------
+    in_bytes = sum(a.nbytes for a in (room.rss, room.rsa, room.cfg, room.clearances, room.offlimits, room.vertices,
+                                      room.surfaceRectangle, room.srf)) + 24
+    out_bytes = args.chains * n * 24 + args.chains * 32
+    k.wrapper_ex(room, args.chains, max(1, args.iterations // 100), seed=7, chain_offset=offset)   # warm
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        res, pts, costs = k.wrapper_ex_raw(room, args.chains, args.iterations, seed=7 + s, chain_offset=offset, lanes_per_chain=args.lanes)
+        e2e_best = float(costs["totalCosts"].max())        # the caller reads the result in place ...
+        k.free(res)                                        # ... and hands it back
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    t = torch.tensor([e2e_wall], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = proposals / float(t[0])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        sm_max_mhz = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or info["sm_clock_khz"] / 1e3)
+        peak_tflops = info["sm_count"] * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+        f_contract, f_live = room.flops_per_proposal(), room.flops_per_proposal(live=True)
+        per_gpu_rate = float(args.chains) * args.iterations * args.steps / kernel_max
+        achieved = per_gpu_rate * f_live / 1e12
+        roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                    "traffic": None,
+                    "flops_per_proposal": {"live": f_live, "contract": f_contract},
+                    "achieved_contract": per_gpu_rate * f_contract / 1e12, "frac_contract": per_gpu_rate * f_contract / 1e12 / peak_tflops,
+                    "kernel": "mh_chain_kernel", "kernel_ms_per_launch": kernel_max * 1e3 / args.steps,
+                    "peak_source": f"FP32 pipe = {info['sm_count']} SMs x 128 lanes x 2 x {sm_max_mhz:.0f} MHz (sm_max_mhz of "
+                                   + ("MEASURED_PEAKS.json" if peaks.get("sm_max_mhz") else "nvidia-smi") + "); HBM is not the bound: "
+                                   "chain state lives in shared memory",
+                    "frac_at_observed_clock": (achieved / (info["sm_count"] * 256 * clocks["sm_mhz"] * 1e6 / 1e12)) if clocks and clocks.get("sm_mhz") else None}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": wall_max * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"config {args.config} ({room.name}): n={n} C={room.C} R={room.R}, {args.chains} chains/GPU x {args.iterations} iterations, all cost terms, beta=2",
+                           "chains_total": total_chains, "lanes_per_chain": args.lanes or "auto", "parallelism": f"chains sharded over {world} GPU(s), NCCL arg-best",
+                           "l2": "256 MiB memset between steps; the chain state lives in shared memory"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                        "call": "KernelWrapperEx (host buffers in, malloc'd result block out)"},
+                "gpu_launches": int(l1 - l0), "roofline": roofline, "clocks": clocks,
+                "best": {"global_chain": int(best[0]), "totalCosts": float(best[1])}, "device": info["name"]}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(room)
+        if not args.no_ref_gpu:
+            try:
+                if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libKernel_ref_nb.so")):
+                    v_wall, v_dev, _ = reference_gpu(args.config, args.ref_chains, args.ref_iterations, 1, 1, timeout_s=120)
+                    line["ref_gpu_baseline"] = {"value": v_wall, "unit": UNIT, "kind": "reference kernel rebuilt for sm_100 (divergent barrier neutralised), blockxDim=64, same GPU",
+                                                "sample": f"{args.ref_chains} chains x {args.ref_iterations} iterations, whole KernelWrapper call; device-event rate {v_dev:.4g}/s"}
+            except Exception as ex:
+                line["ref_gpu_baseline"] = {"unavailable": str(ex)}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

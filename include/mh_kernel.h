@@ -147,15 +147,29 @@ MH_API int KernelResults(mhContext *ctx, point *points, resultCosts *costs);
 /* Device addresses of the result buffers (valid until KernelDestroy), for zero-copy
  * consumers such as a collective over the per-chain costs. */
 MH_API int KernelDeviceResults(mhContext *ctx, void **d_points, void **d_costs);
-/* Run on a caller-provided CUDA stream (a cudaStream_t passed as void*; NULL = own stream). */
+/* Run on a caller-provided CUDA stream (a cudaStream_t passed as void*).  NULL = a stream of the
+ * library's own; to name the legacy default stream pass cudaStreamLegacy, i.e. (void*)0x1. */
 MH_API int KernelSetStream(mhContext *ctx, void *stream);
 /* Index (local to this context) and totalCosts of the chain with the highest totalCosts
  * (the sampler maximises totalCosts, quirk Q10); reduced on the device. */
 MH_API int KernelBest(mhContext *ctx, int *bestChain, float *bestTotal);
+/* Multi-GPU arg-best: writes to the DEVICE address d_key one signed 64-bit key that orders like
+ * (totalCosts of this context's best chain, lower global chain id first).  A MAX all-reduce of
+ * the keys over all ranks (NCCL has no arg-max) yields the global best; KernelDecodeBestKey
+ * recovers the global chain id and its totalCosts.  Asynchronous on the context's stream. */
+MH_API int KernelBestKey(mhContext *ctx, void *d_key);
+MH_API void KernelDecodeBestKey(long long key, unsigned long long *globalChain, float *total);
+/* Restart every chain from the caller's layout (iteration counter back to 0). */
+MH_API int KernelReset(mhContext *ctx);
 /* Milliseconds the device spent in the MH kernels since creation (CUDA events) and how many
  * kernels were launched. */
 MH_API int KernelStats(mhContext *ctx, double *kernel_ms, long long *launches);
 MH_API void KernelDestroy(mhContext *ctx);
+
+/* Device memory is drawn from a pool the library keeps between calls (the reference re-allocates
+ * and frees 12 buffers per call, Kernel.cu:879-967).  KernelTrim returns the cached blocks of
+ * the current device to the driver. */
+MH_API int KernelTrim(void);
 
 /* Library / device facts for harnesses: returns 0 and fills what is non-NULL. */
 MH_API int KernelDeviceInfo(int *smCount, int *smClockKHz, int *ccMajor, int *ccMinor,

@@ -17,7 +17,7 @@ _P = C.c_void_p
 
 EXPORTS = ("KernelWrapper", "KernelWrapperEx", "KernelFree", "KernelLastError", "KernelEvalCosts", "KernelCreate", "KernelRun",
            "KernelRunTraced", "KernelSynchronize", "KernelResults", "KernelDeviceResults", "KernelSetStream", "KernelBest",
-           "KernelStats", "KernelDestroy", "KernelDeviceInfo")
+           "KernelStats", "KernelDestroy", "KernelDeviceInfo", "KernelBestKey", "KernelDecodeBestKey", "KernelReset", "KernelTrim")
 
 
 class KernelError(RuntimeError):
@@ -66,6 +66,10 @@ class Kernel:
             lib.KernelSynchronize.argtypes = [_P]
             lib.KernelResults.argtypes = [_P, _P, _P]
             lib.KernelSetStream.argtypes = [_P, _P]
+            lib.KernelBestKey.argtypes = [_P, _P]
+            lib.KernelReset.argtypes = [_P]
+            lib.KernelDecodeBestKey.argtypes = [C.c_longlong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]
+            lib.KernelDecodeBestKey.restype = None
             Kernel._lib = lib
         self.lib = Kernel._lib
 
@@ -103,6 +107,23 @@ class Kernel:
             self._fail("KernelWrapper")
         return self._unpack(res, n_chains, room.n)
 
+    def wrapper_ex_raw(self, room, n_chains, iterations, **opts):
+        """KernelWrapperEx without the copies of _unpack: returns (result* address, points view,
+        costs view) over the library's malloc'd blocks; the caller must KernelFree the address."""
+        g = np.zeros(1, L.gpuConfig)
+        g["gridxDim"], g["blockxDim"], g["iterations"] = n_chains, 64, iterations
+        o = make_options(**opts)
+        res = self.lib.KernelWrapperEx(*self._room_args(room), _ptr(g), _ptr(o))
+        if not res:
+            self._fail("KernelWrapperEx")
+        r = np.ctypeslib.as_array(C.cast(res, C.POINTER(C.c_uint8)), shape=(n_chains * L.result.itemsize,)).view(L.result)
+        base = int(r["points"][0])
+        pts = np.ctypeslib.as_array(C.cast(base, C.POINTER(C.c_uint8)), shape=(n_chains * room.n * L.point.itemsize,)).view(L.point)
+        return res, pts.reshape(n_chains, room.n), r["costs"]
+
+    def free(self, res):
+        self.lib.KernelFree(res)
+
     def wrapper_ex(self, room, n_chains, iterations, **opts):
         g = np.zeros(1, L.gpuConfig)
         g["gridxDim"], g["blockxDim"], g["iterations"] = n_chains, 64, iterations
@@ -128,6 +149,11 @@ class Kernel:
         if self.lib.KernelDeviceInfo(C.byref(sm), C.byref(khz), C.byref(ma), C.byref(mi), name, 256) != 0:
             self._fail("KernelDeviceInfo")
         return {"sm_count": sm.value, "sm_clock_khz": khz.value, "cc": (ma.value, mi.value), "name": name.value.decode()}
+
+    def decode_best_key(self, key):
+        g, t = C.c_ulonglong(), C.c_float()
+        self.lib.KernelDecodeBestKey(C.c_longlong(int(key)), C.byref(g), C.byref(t))
+        return g.value, t.value
 
     def create(self, room, n_chains, **opts):
         return Context(self, room, n_chains, **opts)
@@ -172,6 +198,10 @@ class Context:
         return dp.value, dc.value
 
     def set_stream(self, stream_handle):
+        """stream_handle: a cudaStream_t as an integer (e.g. torch.cuda.current_stream().cuda_stream).
+        torch reports the legacy default stream as 0; the C ABI names it cudaStreamLegacy = 0x1."""
+        if not stream_handle:
+            stream_handle = 1
         if self.k.lib.KernelSetStream(self.h, _P(stream_handle)) != 0:
             self.k._fail("KernelSetStream")
 
@@ -180,6 +210,15 @@ class Context:
         if self.k.lib.KernelBest(self.h, C.byref(i), C.byref(t)) != 0:
             self.k._fail("KernelBest")
         return i.value, t.value
+
+    def best_key(self, d_key):
+        """d_key: device address of one int64 (e.g. a torch tensor's data_ptr())."""
+        if self.k.lib.KernelBestKey(self.h, _P(d_key)) != 0:
+            self.k._fail("KernelBestKey")
+
+    def reset(self):
+        if self.k.lib.KernelReset(self.h) != 0:
+            self.k._fail("KernelReset")
 
     def stats(self):
         ms, n = C.c_double(), C.c_longlong()

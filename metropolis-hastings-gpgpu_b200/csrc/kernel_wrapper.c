@@ -24,6 +24,7 @@
 #include "mh_abi.h"
 
 #define MH_TLS __thread
+#define MH_MAX_BLOCKS_PER_SM 5 /* 128-thread blocks at the chain kernel's register count */
 
 static MH_TLS char g_err[512];
 
@@ -259,14 +260,20 @@ static void leave_device(int want, int prev)
     if (want >= 0 && want != prev) mhdev_set_device(prev);
 }
 
-/* Lanes per chain.  Fewer lanes waste fewer slots of the last row pass (efficiency
- * n / (G*ceil(n/G))) but put more chains, hence more shared memory, behind every warp and need
- * more chains to fill the machine.  Score = lane efficiency x how well the resident warps cover
- * the SMs; see DESIGN.md for the measured table behind the constants. */
+/* Lanes per chain.  A warp advances 32/G chains per proposal step at a cost of roughly
+ * O + rows*(12n + 8C + 100) warp instructions, rows = ceil(n/G) and O ~ 450 for the work every
+ * lane repeats (Philox, propose, accept, reductions), so the cost per chain is
+ * G*(O + rows*(12n+8C+100))/32: narrow groups win on small rooms, and lose nothing on big ones
+ * except shared memory -- which caps the resident warps, and throughput grows about linearly
+ * with resident warps up to ~18 per SM (measured on B200).  Pick the width
+ * with the best modelled throughput; MH_LANES or mhOptions.lanes_per_chain override. */
 static int choose_lanes(int n, int C, int smem_words, int n_chains, int requested)
 {
     int max_block = 0, max_sm = 0, sms = 0;
-    if (mhdev_device_limits(&max_block, &max_sm, &sms, NULL, NULL, NULL, NULL, 0)) return -1;
+    if (mhdev_device_limits(&max_block, &max_sm, &sms, NULL, NULL, NULL, NULL, 0)) {
+        set_err("%s failed: %s", "device query", mhdev_device_limits(&max_block, &max_sm, &sms, NULL, NULL, NULL, NULL, 0));
+        return -1;
+    }
     const char *env = getenv("MH_LANES");
     if (requested <= 0 && env) requested = atoi(env);
     static const int cand[6] = { 32, 16, 8, 4, 2, 1 };
@@ -278,18 +285,18 @@ static int choose_lanes(int n, int C, int smem_words, int n_chains, int requeste
         if (bytes < 0 || bytes > max_block) continue;
         if (requested == G) return G;
         int blocks_per_sm = max_sm / (bytes + 1024);
-        if (blocks_per_sm > 5) blocks_per_sm = 5; /* register-limited: ~96 regs x 128 threads */
+        if (blocks_per_sm > MH_MAX_BLOCKS_PER_SM) blocks_per_sm = MH_MAX_BLOCKS_PER_SM; /* register-limited */
         if (blocks_per_sm < 1) blocks_per_sm = 1;
         const double cap_warps = 4.0 * blocks_per_sm;
         const double cpw = 32.0 / G;
         const double warps_total = ceil((double)n_chains / cpw);
         double per_sm = warps_total / (double)sms;
         if (per_sm > cap_warps) per_sm = cap_warps;
-        const double cover = per_sm >= 12.0 ? 1.0 : per_sm / 12.0;
+        const double cover = per_sm >= 18.0 ? 1.0 : per_sm / 18.0;
         const double rows = ceil((double)n / G);
-        const double eff = (double)n / (G * rows);
-        const double score = eff * cover;
-        if (score > best_score * 1.02) { /* ties go to the wider group (less shared memory) */
+        const double cost = G * (450.0 + rows * (12.0 * n + 8.0 * C + 100.0)) / 32.0;
+        const double score = cover / cost;
+        if (score > best_score * 1.03) { /* near-ties go to the wider group (less shared memory) */
             best_score = score;
             best = G;
         }
@@ -301,9 +308,10 @@ static int choose_lanes(int n, int C, int smem_words, int n_chains, int requeste
 static void ctx_free(mhContext *c)
 {
     if (!c) return;
-    mhdev_free(c->d_problem); mhdev_free(c->d_x); mhdev_free(c->d_y); mhdev_free(c->d_rot); mhdev_free(c->d_cur);
-    mhdev_free(c->d_best); mhdev_free(c->d_beta); mhdev_free(c->d_perm); mhdev_free(c->d_points); mhdev_free(c->d_costs);
-    mhdev_free(c->d_scratch);
+    void *st = c->stream;
+    mhdev_free(c->d_problem, st); mhdev_free(c->d_x, st); mhdev_free(c->d_y, st); mhdev_free(c->d_rot, st); mhdev_free(c->d_cur, st);
+    mhdev_free(c->d_best, st); mhdev_free(c->d_beta, st); mhdev_free(c->d_perm, st); mhdev_free(c->d_points, st);
+    mhdev_free(c->d_costs, st); mhdev_free(c->d_scratch, st);
     for (int i = 0; i < c->n_ev; i++) { mhdev_event_destroy(c->ev[i].e0); mhdev_event_destroy(c->ev[i].e1); }
     free(c->ev);
     if (c->own_stream) mhdev_stream_destroy(c->stream);
@@ -367,17 +375,17 @@ MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationship
     CU(mhdev_stream_create(&c->stream));
     c->own_stream = 1;
     const size_t cn = (size_t)nChains * (size_t)c->n;
-    CU(mhdev_malloc(&c->d_problem, 4 * (size_t)c->problem_words));
-    CU(mhdev_malloc((void **)&c->d_x, 4 * cn));
-    CU(mhdev_malloc((void **)&c->d_y, 4 * cn));
-    CU(mhdev_malloc((void **)&c->d_rot, 4 * cn));
-    CU(mhdev_malloc((void **)&c->d_perm, 2 * cn));
-    CU(mhdev_malloc((void **)&c->d_cur, 4 * (size_t)nChains));
-    CU(mhdev_malloc((void **)&c->d_best, 4 * (size_t)nChains));
-    CU(mhdev_malloc((void **)&c->d_beta, 4 * (size_t)nChains));
-    CU(mhdev_malloc(&c->d_points, sizeof(point) * cn));
-    CU(mhdev_malloc(&c->d_costs, sizeof(resultCosts) * (size_t)nChains));
-    CU(mhdev_malloc(&c->d_scratch, 64));
+    CU(mhdev_malloc(&c->d_problem, 4 * (size_t)c->problem_words, c->stream));
+    CU(mhdev_malloc((void **)&c->d_x, 4 * cn, c->stream));
+    CU(mhdev_malloc((void **)&c->d_y, 4 * cn, c->stream));
+    CU(mhdev_malloc((void **)&c->d_rot, 4 * cn, c->stream));
+    CU(mhdev_malloc((void **)&c->d_perm, 2 * cn, c->stream));
+    CU(mhdev_malloc((void **)&c->d_cur, 4 * (size_t)nChains, c->stream));
+    CU(mhdev_malloc((void **)&c->d_best, 4 * (size_t)nChains, c->stream));
+    CU(mhdev_malloc((void **)&c->d_beta, 4 * (size_t)nChains, c->stream));
+    CU(mhdev_malloc(&c->d_points, sizeof(point) * cn, c->stream));
+    CU(mhdev_malloc(&c->d_costs, sizeof(resultCosts) * (size_t)nChains, c->stream));
+    CU(mhdev_malloc(&c->d_scratch, 64, c->stream));
     CU(mhdev_h2d(c->d_problem, P.blob, 4 * (size_t)c->problem_words, c->stream));
     if (c->opt.tempering_rungs > 1) {
         /* rung r of every ladder starts at beta_start * (beta_end/beta_start)^(r/(T-1)) */
@@ -480,7 +488,7 @@ static int run_iterations(mhContext *c, int iterations, mhTraceEntry *trace)
     if (!c || iterations < 0) { set_err("", "bad arguments", 0); return -1; }
     CU(enter_device(c->device, &prev));
     if (c->opt.schedule_length <= 0 && c->opt.schedule != MH_SCHEDULE_CONSTANT) c->opt.schedule_length = iterations;
-    if (trace) CU(mhdev_malloc(&d_trace, sizeof(mhTraceEntry) * (size_t)iterations * (size_t)c->n_chains));
+    if (trace) CU(mhdev_malloc(&d_trace, sizeof(mhTraceEntry) * (size_t)iterations * (size_t)c->n_chains, c->stream));
     if (c->opt.tempering_rungs > 1) {
         /* segments end on exchange boundaries; the whole ladder lives in this context */
         const uint64_t ex = (uint64_t)c->opt.exchange_interval;
@@ -509,7 +517,7 @@ static int run_iterations(mhContext *c, int iterations, mhTraceEntry *trace)
     }
     rc = 0;
 fail:
-    if (d_trace) { mhdev_stream_sync(c->stream); mhdev_free(d_trace); }
+    if (d_trace) { mhdev_stream_sync(c->stream); mhdev_free(d_trace, c->stream); }
     if (prev >= 0) leave_device(c->device, prev);
     return rc;
 }
@@ -595,7 +603,7 @@ MH_API int KernelSetStream(mhContext *ctx, void *stream)
         ctx->own_stream = 0;
     }
     ctx->stream = stream;
-    if (!stream) {
+    if (!stream) { /* NULL = a stream of our own; the legacy default stream is the handle 0x1 */
         int prev = -1, e = enter_device(ctx->device, &prev);
         if (!e) e = mhdev_stream_create(&ctx->stream);
         if (prev >= 0) leave_device(ctx->device, prev);
@@ -623,6 +631,41 @@ MH_API int KernelBest(mhContext *ctx, int *bestChain, float *bestTotal)
 fail:
     if (prev >= 0) leave_device(ctx->device, prev);
     return rc;
+}
+
+MH_API int KernelBestKey(mhContext *ctx, void *d_key)
+{
+    int prev = -1, rc = -1;
+    g_err[0] = 0;
+    if (!ctx || !d_key) { set_err("", "bad arguments", 0); return -1; }
+    CU(enter_device(ctx->device, &prev));
+    CU(ensure_scored(ctx));
+    CU(mhdev_launch_argmax(ctx->d_costs, ctx->n_chains, ctx->d_scratch, ctx->stream));
+    CU(mhdev_launch_bestkey(ctx->d_scratch, ctx->opt.chain_offset, 1, d_key, ctx->stream));
+    ctx->launches += 2;
+    rc = 0;
+fail:
+    if (prev >= 0) leave_device(ctx->device, prev);
+    return rc;
+}
+
+MH_API void KernelDecodeBestKey(long long key, unsigned long long *globalChain, float *total)
+{
+    const uint64_t k = (uint64_t)key ^ 0x8000000000000000ull;
+    uint32_t u = (uint32_t)(k >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    if (total) memcpy(total, &u, 4);
+    if (globalChain) *globalChain = (unsigned long long)(0xFFFFFFFFu - (uint32_t)k);
+}
+
+MH_API int KernelReset(mhContext *ctx)
+{
+    g_err[0] = 0;
+    if (!ctx) { set_err("", "null context", 0); return -1; }
+    ctx->fresh = 1;
+    ctx->it_done = 0;
+    ctx->costs_dirty = 1;
+    return 0;
 }
 
 MH_API int KernelStats(mhContext *ctx, double *kernel_ms, long long *launches)
@@ -668,21 +711,39 @@ MH_API result *KernelWrapperEx(const relationshipStruct *rss, const relationship
         return NULL;
     }
     const int n = srf->nObjs;
+    const int timing = getenv("MH_TIMING") != NULL;
+    struct timespec ts[6];
+    clock_gettime(CLOCK_MONOTONIC, &ts[0]);
     mhContext *c = KernelCreate(rss, rsa, cfg, clearances, offlimits, vertices, surfaceRectangle, srf, chains, opt);
     if (!c) return NULL;
+    clock_gettime(CLOCK_MONOTONIC, &ts[1]);
     /* Kernel.cu:928, 970: ONE block of points and one array of results, both plain malloc */
     point *pts = (point *)malloc(sizeof(point) * (size_t)chains * (size_t)n);
     result *res = (result *)malloc(sizeof(result) * (size_t)chains);
     resultCosts *costs = (resultCosts *)malloc(sizeof(resultCosts) * (size_t)chains);
     if (!pts || !res || !costs) { set_err("", "out of host memory", 0); goto fail; }
+    clock_gettime(CLOCK_MONOTONIC, &ts[2]);
     if (KernelRun(c, iterations)) goto fail;
+    if (timing) KernelSynchronize(c);
+    clock_gettime(CLOCK_MONOTONIC, &ts[3]);
     if (KernelResults(c, pts, costs)) goto fail;
+    clock_gettime(CLOCK_MONOTONIC, &ts[4]);
     for (int i = 0; i < chains; i++) {
         res[i].points = pts + (size_t)i * (size_t)n; /* Kernel.cu:981 */
         res[i].costs = costs[i];
     }
     free(costs);
+    struct timespec td;
+    clock_gettime(CLOCK_MONOTONIC, &td);
     KernelDestroy(c);
+    clock_gettime(CLOCK_MONOTONIC, &ts[5]);
+    if (timing) fprintf(stderr, "[mh] destroy alone %.2f ms\n", 1e3 * (double)(ts[5].tv_sec - td.tv_sec) + 1e-6 * (double)(ts[5].tv_nsec - td.tv_nsec));
+    if (timing) {
+        double d[5];
+        for (int i = 0; i < 5; i++) d[i] = 1e3 * (double)(ts[i + 1].tv_sec - ts[i].tv_sec) + 1e-6 * (double)(ts[i + 1].tv_nsec - ts[i].tv_nsec);
+        fprintf(stderr, "[mh] create %.2f ms, host alloc %.2f ms, run %.2f ms, results %.2f ms, assemble+destroy %.2f ms\n", d[0], d[1], d[2],
+                d[3], d[4]);
+    }
     return res;
 fail:
     free(pts); free(res); free(costs);
@@ -738,9 +799,9 @@ MH_API int KernelEvalCosts(const relationshipStruct *rss, const relationshipAngl
     const int lanes = choose_lanes(n, P.h->C, P.h->smem_words, nLayouts, 0);
     if (lanes < 0) goto fail;
     CU(mhdev_stream_create(&stream));
-    CU(mhdev_malloc(&d_problem, 4 * (size_t)P.h->total_words));
-    CU(mhdev_malloc(&d_points, sizeof(point) * cn));
-    CU(mhdev_malloc(&d_costs, sizeof(resultCosts) * (size_t)nLayouts));
+    CU(mhdev_malloc(&d_problem, 4 * (size_t)P.h->total_words, stream));
+    CU(mhdev_malloc(&d_points, sizeof(point) * cn, stream));
+    CU(mhdev_malloc(&d_costs, sizeof(resultCosts) * (size_t)nLayouts, stream));
     CU(mhdev_h2d(d_problem, P.blob, 4 * (size_t)P.h->total_words, stream));
     CU(mhdev_h2d(d_points, pts, sizeof(point) * cn, stream));
     CU(mhdev_launch_score(d_problem, P.h->smem_words, n, P.h->C, P.h->R, nLayouts, lanes, d_points, d_costs, stream));
@@ -749,11 +810,19 @@ MH_API int KernelEvalCosts(const relationshipStruct *rss, const relationshipAngl
     rc = 0;
 fail:
     if (stream) mhdev_stream_sync(stream);
-    mhdev_free(d_problem); mhdev_free(d_points); mhdev_free(d_costs);
+    mhdev_free(d_problem, stream); mhdev_free(d_points, stream); mhdev_free(d_costs, stream);
     if (stream) mhdev_stream_destroy(stream);
     free(pts);
     free(P.blob);
     return rc;
+}
+
+MH_API int KernelTrim(void)
+{
+    g_err[0] = 0;
+    int e = mhdev_trim();
+    if (e) { set_err("%s failed: %s", "pool trim", e); return -1; }
+    return 0;
 }
 
 MH_API int KernelDeviceInfo(int *smCount, int *smClockKHz, int *ccMajor, int *ccMinor, char *name, int nameLen)

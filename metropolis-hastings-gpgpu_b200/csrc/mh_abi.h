@@ -95,6 +95,8 @@ int mhdev_launch_exchange(int n_chains, uint64_t chain_offset, uint64_t chain_st
                           uint64_t gather_base, float *d_beta, void *stream);
 /* arg-max of totalCosts over the context's chains: d_out = {float total, int32 chain}. */
 int mhdev_launch_argmax(const void *d_costs, int n_chains, void *d_out, void *stream);
+/* d_key (device int64) = order-preserving (totalCosts, global chain id) key of the arg-max result. */
+int mhdev_launch_bestkey(const void *d_argmax_out, uint64_t chain_offset, uint64_t chain_stride, void *d_key, void *stream);
 /* Largest dynamic shared memory per block and SM count / clock of the current device. */
 int mhdev_device_limits(int *max_smem_per_block, int *max_smem_per_sm, int *sm_count, int *clock_khz, int *cc_major,
                         int *cc_minor, char *name, int name_len);
@@ -103,8 +105,9 @@ int mhdev_chain_smem_bytes(int smem_words, int n, int C, int lanes, int warps_pe
 /* raw runtime helpers */
 int mhdev_get_device(int *dev);
 int mhdev_set_device(int dev);
-int mhdev_malloc(void **p, size_t bytes);
-void mhdev_free(void *p);
+int mhdev_malloc(void **p, size_t bytes, void *stream); /* stream-ordered, from the library's pool */
+void mhdev_free(void *p, void *stream);
+int mhdev_trim(void);                                    /* return cached blocks to the driver  */
 int mhdev_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int mhdev_d2h(void *dst, const void *src, size_t bytes, void *stream);
 int mhdev_memset(void *dst, int value, size_t bytes, void *stream);

@@ -13,6 +13,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <mutex>
 
 #include "mh_abi.h"
 #include "mh_costs.cuh"
@@ -332,6 +335,20 @@ __global__ void mh_argmax_kernel(const Costs8 *__restrict__ costs, int n, float 
     }
 }
 
+// Packs the context's best chain for a MAX all-reduce: NCCL has no arg-max, so the totalCosts
+// (made order-preserving as an unsigned integer) goes in the high word and the complemented
+// global chain id in the low word (ties go to the lower id); the top bit is flipped so that a
+// SIGNED 64-bit MAX orders the keys correctly.
+__global__ void mh_bestkey_kernel(const float *__restrict__ best_total, const int *__restrict__ best_idx, uint64_t chain_offset,
+                                  uint64_t chain_stride, long long *__restrict__ key)
+{
+    uint32_t u = __float_as_uint(*best_total);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    const uint64_t g = chain_offset + (uint64_t)(*best_idx) * chain_stride;
+    const uint64_t k = ((uint64_t)u << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)g);
+    *key = (long long)(k ^ 0x8000000000000000ull);
+}
+
 template <int G> static int launch_chains_g(const mhLaunch &L)
 {
     using WS = WarpState<G>;
@@ -428,6 +445,14 @@ int mhdev_launch_argmax(const void *d_costs, int n_chains, void *d_out, void *st
     return (int)cudaGetLastError();
 }
 
+int mhdev_launch_bestkey(const void *d_argmax_out, uint64_t chain_offset, uint64_t chain_stride, void *d_key, void *stream)
+{
+    const float *f = static_cast<const float *>(d_argmax_out);
+    mh::mh_bestkey_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(f, reinterpret_cast<const int *>(f + 1), chain_offset,
+                                                                        chain_stride, static_cast<long long *>(d_key));
+    return (int)cudaGetLastError();
+}
+
 int mhdev_device_limits(int *max_smem_per_block, int *max_smem_per_sm, int *sm_count, int *clock_khz, int *cc_major, int *cc_minor,
                         char *name, int name_len)
 {
@@ -452,8 +477,61 @@ int mhdev_device_limits(int *max_smem_per_block, int *max_smem_per_sm, int *sm_c
 
 int mhdev_get_device(int *dev) { return (int)cudaGetDevice(dev); }
 int mhdev_set_device(int dev) { return (int)cudaSetDevice(dev); }
-int mhdev_malloc(void **p, size_t bytes) { return (int)cudaMalloc(p, bytes ? bytes : 16); }
-void mhdev_free(void *p) { if (p) cudaFree(p); }
+
+// Device memory comes from a stream-ordered pool owned by the library, one per device, that
+// keeps freed blocks for the next call (release threshold = unlimited): the reference pays 12
+// cudaMalloc + cudaFree per call (Kernel.cu:879-967), and on this driver a cudaFree of the
+// ~130 MB a 65536-chain call needs was measured at up to 600 ms.  KernelTrim() gives the cache back.
+static std::mutex g_pool_mutex;
+static cudaMemPool_t g_pools[64];
+static bool g_pool_ready[64];
+
+static cudaError_t pool_for_current_device(cudaMemPool_t *pool)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pool_ready[dev]) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        e = cudaMemPoolCreate(&g_pools[dev], &props);
+        if (e != cudaSuccess) return e;
+        unsigned long long keep = ~0ull;
+        e = cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) return e;
+        g_pool_ready[dev] = true;
+    }
+    *pool = g_pools[dev];
+    return cudaSuccess;
+}
+
+int mhdev_malloc(void **p, size_t bytes, void *stream)
+{
+    cudaMemPool_t pool;
+    cudaError_t e = pool_for_current_device(&pool);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaMallocFromPoolAsync(p, bytes ? bytes : 16, pool, static_cast<cudaStream_t>(stream));
+}
+void mhdev_free(void *p, void *stream) { if (p) cudaFreeAsync(p, static_cast<cudaStream_t>(stream)); }
+int mhdev_trim(void)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (dev >= 0 && dev < 64 && g_pool_ready[dev]) {
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return (int)e;
+        return (int)cudaMemPoolTrimTo(g_pools[dev], 0);
+    }
+    return 0;
+}
 int mhdev_h2d(void *dst, const void *src, size_t bytes, void *stream)
 {
     return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));

@@ -1,0 +1,66 @@
+"""Multi-GPU host logic: chain sharding and the global-best reduction.
+
+Chains are independent, so ranks shard contiguous ranges of the GLOBAL
+chain id and never exchange data on the sampling path.  The only collective is the arg-best at
+the end of a run: NCCL has no MINLOC/MAXLOC, so each rank packs (order-preserving totalCosts,
+complemented global chain id) into one signed 64-bit key on its device (KernelBestKey), the
+keys are MAX-all-reduced (8 bytes), and the owner of the winning chain broadcasts its n x 24 B
+layout.  torch.distributed is plumbing only; the packing and the arg-max run in libKernel.so.
+"""
+import numpy as np
+
+
+def shard(total_chains, rank, world):
+    """Contiguous range [offset, offset+count) of global chain ids owned by `rank`."""
+    base, rem = divmod(total_chains, world)
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, count
+
+
+def owner_of(global_chain, total_chains, world):
+    base, rem = divmod(total_chains, world)
+    edge = rem * (base + 1)
+    if global_chain < edge:
+        return global_chain // (base + 1)
+    return rem + (global_chain - edge) // base
+
+
+def pack_best_key(total, global_chain):
+    """Host restatement of mh_bestkey_kernel (csrc/mh_kernels.cu) for CPU tests."""
+    u = int(np.float32(total).view(np.uint32))
+    u = (~u & 0xFFFFFFFF) if (u & 0x80000000) else (u | 0x80000000)
+    k = (u << 32) | (0xFFFFFFFF - (int(global_chain) & 0xFFFFFFFF))
+    k ^= 0x8000000000000000
+    return k - (1 << 64) if k >= (1 << 63) else k
+
+
+class DeviceBytes:
+    """Zero-copy torch view of device memory owned by libKernel.so."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def device_view(ptr, nbytes, device):
+    import torch
+    return torch.as_tensor(DeviceBytes(ptr, nbytes), device=device)
+
+
+def global_best(kernel, ctx, n, offset, total_chains, rank, world, device, dist=None):
+    """Returns (global chain id, totalCosts, layout bytes tensor of n*24 B) on every rank."""
+    import torch
+    key = torch.zeros(1, dtype=torch.int64, device=device)
+    ctx.best_key(key.data_ptr())
+    if dist is not None and world > 1:
+        dist.all_reduce(key, op=dist.ReduceOp.MAX)
+    g, total = kernel.decode_best_key(int(key.item()))
+    owner = owner_of(g, total_chains, world)
+    layout = torch.empty(n * 24, dtype=torch.uint8, device=device)
+    if rank == owner:
+        d_points, _ = ctx.device_results()
+        view = device_view(d_points, ctx.n_chains * n * 24, device)
+        layout.copy_(view[(g - offset) * n * 24:(g - offset + 1) * n * 24])
+    if dist is not None and world > 1:
+        dist.broadcast(layout, src=owner)
+    return g, total, layout

@@ -14,9 +14,26 @@
  *   RefTimedWrapper    -- KernelWrapper bracketed by CUDA events (whole call, on the device
  *                         clock), for the throughput baseline.
  */
+#ifdef REF_NO_DIVERGENT_BARRIER
+/* Variant libKernel_ref_nb.so.  The reference's Copy() ends in __syncthreads() (Kernel.cu:747)
+ * and is called under `if (Accept(...))` (Kernel.cu:819-824), where every thread of the block
+ * decides with its own RNG state: a divergent block barrier.  On sm_70+ (independent thread
+ * scheduling) the threads that skip the branch wait at the warp reconvergence point for the
+ * ones parked in the barrier -- observed on B200: the unmodified kernel never returns for
+ * blockxDim > 1.  This variant neutralises that ONE barrier (by source line, through the
+ * preprocessor; the reference file itself is untouched) so that the reference's own launch
+ * shape (blockxDim = 64, Kernel.cu:1191) can be timed.  The other four barriers stay. */
+#include <cuda_runtime.h>
+static __device__ __forceinline__ void ref_real_barrier() { __syncthreads(); }
+static __device__ __forceinline__ void ref_barrier(int line) { if (line != 747) ref_real_barrier(); }
+#define __syncthreads() ref_barrier(__LINE__)
+#endif
 #define main ref_main
 #include "Kernel.cu"
 #undef main
+#ifdef REF_NO_DIVERGENT_BARRIER
+#undef __syncthreads
+#endif
 
 __global__ void refCostsKernel(resultCosts *out, Surface *srf, positionAndRotation *layouts, int nLayouts,
                                relationshipStruct *rs, relationshipAngleStruct *ra, vertex *vertices,

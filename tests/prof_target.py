@@ -1,0 +1,16 @@
+"""Profiling target: one warm-up launch and one measured launch of the chain kernel.
+usage: prof_target.py <config id> <chains> <iterations> [lanes]"""
+import importlib, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("metropolis-hastings-gpgpu_b200")
+cid, chains, iters = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+lanes = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+k = pkg.Kernel()
+room = pkg.synth.make_config(cid)
+with k.create(room, chains, seed=1, lanes_per_chain=lanes) as ctx:
+    ctx.run(iters); ctx.synchronize(); ctx.stats()
+    ctx.reset()
+    t0 = time.time(); ctx.run(iters); ctx.synchronize(); dt = time.time() - t0
+    ms, n = ctx.stats()
+    print(f"cfg{cid} chains={chains} iters={iters} lanes={lanes}: kernel {ms:.2f} ms, {chains*iters/(ms*1e-3):.4e} proposals/s")

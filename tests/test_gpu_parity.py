@@ -102,6 +102,21 @@ def test_every_lane_width_gives_the_same_costs(kernel, oracle, lanes, monkeypatc
     assert_costs_close(room, got, ref, skip_pair=near_jump(oracle, room, lay))
 
 
+def test_costs_match_the_references_own_device_code(kernel):
+    """GPU vs GPU: the reference's Costs() (Kernel.cu:516-550) compiled from the reference tree and
+    run on this device (oracle/_ref/libKernel_ref.so, RefCostsGPU) against KernelEvalCosts."""
+    from oracle_lib import RefGPU, Oracle, ref_gpu_path
+    if not os.path.exists(ref_gpu_path()):
+        pytest.skip("oracle/_ref/libKernel_ref.so not built")
+    ref, o = RefGPU(), Oracle()
+    for cid, count in ((1, 1024), (2, 512), (3, 256)):
+        room = S.make_config(cid)
+        lay = S.random_layouts(room, count, 17 + cid)
+        got = kernel.eval_costs(room, lay)
+        exp = ref.costs_gpu(room, lay)
+        assert_costs_close(room, got, exp, skip_pair=near_jump(o, room, lay))
+
+
 def test_main_fixture_known_answer(kernel):
     room = S.reference_main_fixture()
     c = kernel.eval_costs(room, room.cfg)[0]
