@@ -25,7 +25,8 @@ class KernelError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libKernel.so")
+    """MH_LIB lets a development probe load an experimental build; the product is libKernel.so."""
+    return os.environ.get("MH_LIB") or os.path.join(_HERE, "libKernel.so")
 
 
 def _ptr(a):

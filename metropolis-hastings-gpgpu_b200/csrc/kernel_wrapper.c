@@ -24,7 +24,7 @@
 #include "mh_abi.h"
 
 #define MH_TLS __thread
-#define MH_MAX_BLOCKS_PER_SM 5 /* 128-thread blocks at the chain kernel's register count */
+#define MH_MAX_BLOCKS_PER_SM 5 /* 128-thread blocks at the chain kernel's register cap (MH_MIN_BLOCKS in mh_kernels.cu) */
 
 static MH_TLS char g_err[512];
 

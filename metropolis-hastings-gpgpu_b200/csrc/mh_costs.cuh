@@ -1,12 +1,13 @@
 // mh_costs.cuh -- the Merrell et al. cost terms of the reference (Kernel.cu:162-550), written
 // for a group of G lanes that owns one layout ("chain").
 //
-// Data layout.  A warp holds CPW = 32/G chains.  Chain state (x, y, rotY per object) lives in
-// shared memory, interleaved by chain so that, for a fixed object j, the CPW chains of a warp
-// sit in consecutive banks:   X[j*CPW + c].   In the pair loops every lane of a group reads
-// the same word (a broadcast) and different groups read neighbouring words: conflict-free.
-// In the lane-strided O(n) loops lane (c, g) touches object g + G*k -> word (g+Gk)*CPW + c:
-// the 32 lanes of a warp cover 32 consecutive words: conflict-free.
+// Data layout.  A warp holds CPW = 32/G chains.  Chain state lives in shared memory as one
+// float4 per object, {x, y, rotY, f} with f = the object's memoised focal-point cosine,
+// interleaved by chain:   P4[j*CPW + c].   In the pair loops every lane of a group reads the
+// same 16 bytes (a broadcast) with ONE LDS.128 whose address advances by the compile-time
+// constant CPW*16 per column, so an unrolled loop needs no address arithmetic; the CPW groups
+// of a warp read CPW consecutive float4s.  In the lane-strided O(n) loops lane (c, g) touches
+// object g + G*k -> float4 (g+Gk)*CPW + c: the 32 lanes cover 32 consecutive float4s.
 //
 // The O(n^2) and O(C n) terms are row-parallel: lane g owns rows i = g, g+G, ... and walks
 // all columns, keeping the running max / sum in registers; one xor-shuffle tree per term per
@@ -24,7 +25,13 @@
 
 #include "mh_abi.h"
 
+#ifndef MH_SYM_UNROLL
+#define MH_SYM_UNROLL 8
+#endif
+
 namespace mh {
+
+constexpr int kSymUnroll = MH_SYM_UNROLL; // columns per trip of the symmetry loop
 
 struct SmemProblem {
     const mhProblemHeader *h;
@@ -60,19 +67,17 @@ __device__ __forceinline__ SmemProblem bind_problem(const float *base)
 // Per-warp chain state in shared memory.
 template <int G> struct WarpState {
     static constexpr int CPW = 32 / G;
-    float *X, *Y, *Rt;
-    float4 *CB;     // clearance AABBs of the layout under evaluation, [C][CPW]
-    uint16_t *perm; // [n][CPW]
+    float4 *P4;     // [n][CPW] {x, y, rotY, focal cosine}
+    float4 *CB;     // [C][CPW] clearance AABBs of the layout under evaluation
+    uint16_t *perm; // [n][CPW] which original object's z/rotX/rotZ sits in slot i
     __device__ __forceinline__ static int at(int j, int c) { return j * CPW + c; }
     // words of shared memory one warp needs
-    __host__ __device__ static int words(int n, int C) { return (CPW * (3 * n + 4 * C) + (CPW * n + 1) / 2 + 3) & ~3; }
+    __host__ __device__ static int words(int n, int C) { return (CPW * (4 * n + 4 * C) + (CPW * n + 1) / 2 + 3) & ~3; }
     __device__ __forceinline__ void bind(float *base, int n, int C)
     {
-        CB = reinterpret_cast<float4 *>(base); // keep the float4 array 16-byte aligned
-        X = base + 4 * C * CPW;
-        Y = X + n * CPW;
-        Rt = Y + n * CPW;
-        perm = reinterpret_cast<uint16_t *>(Rt + n * CPW);
+        P4 = reinterpret_cast<float4 *>(base);
+        CB = P4 + n * CPW;
+        perm = reinterpret_cast<uint16_t *>(CB + C * CPW);
     }
 };
 
@@ -141,12 +146,28 @@ __device__ __forceinline__ float outside_room(float4 b, const mhProblemHeader *h
     return e;
 }
 
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// cos(phi) of one object, phi = atan2(fy - y, fx - x) - rot + PI/2 (Kernel.cu:185-188, 271-277).
+// A pure function of that object's state, so it is memoised in the .w lane of its float4 and
+// recomputed only for the one or two objects a proposal moves.
+__device__ __forceinline__ float focal_cos(const mhProblemHeader *h, float x, float y, float rot)
+{
+    return cosf(atan2f(h->focal_y - y, h->focal_x - x) - rot + h->half_pi);
+}
+
 // All terms of one layout.  Every lane of the warp must call this (it synchronises the warp);
 // on return every lane of a group holds the group's totals.
 template <int G, bool WITH_OFFLIMITS>
 __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState<G> &S, const int c, const int g, RawTerms &t)
 {
     using WS = WarpState<G>;
+    constexpr int CPW = WS::CPW;
     const mhProblemHeader *h = P.h;
     const int n = h->n, C = h->C, R = h->R;
     float surf = 0.f, clr = 0.f, sym = 0.f, vbx = 0.f, vby = 0.f, focal = 0.f, off = 0.f, pw = 0.f, pa = 0.f;
@@ -156,57 +177,71 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
     for (int k = g; k < C; k += G) {
         const float4 kb = P.clr_box[k];
         const float v0 = P.clr_v0x[k];
-        const int src = P.clr_src[k];
-        S.CB[WS::at(k, c)] = box_at(kb, v0, S.X[WS::at(src, c)], S.Y[WS::at(src, c)]);
-        surf += outside_room(box_at(kb, v0, S.X[WS::at(k, c)], S.Y[WS::at(k, c)]), h);
+        const float2 ps = *reinterpret_cast<const float2 *>(&S.P4[WS::at(P.clr_src[k], c)]);
+        const float2 pk = *reinterpret_cast<const float2 *>(&S.P4[WS::at(k, c)]);
+        S.CB[WS::at(k, c)] = box_at(kb, v0, ps.x, ps.y);
+        surf += outside_room(box_at(kb, v0, pk.x, pk.y), h);
     }
     __syncwarp();
 
     // ---- rows: one object per lane per pass ----------------------------------------------------
     const float ux = h->ux, uy = h->uy, fdotu = h->fdotu, tfr = h->two_focal_rot;
-    const float pi_cmp = h->pi_cmp, two_pi = h->two_pi;
+    const float pi_cmp = h->pi_cmp, two_pi = h->two_pi, pi_f = 0.5f * h->two_pi;
+    const float4 *Pc = S.P4 + c, *CBc = S.CB + c;
     for (int i = g; i < n; i += G) {
-        const float xi = S.X[WS::at(i, c)], yi = S.Y[WS::at(i, c)], ri = S.Rt[WS::at(i, c)];
-        // visual balance partial sums (Kernel.cu:199-202)
+        const float4 pi = Pc[i * CPW];
+        // visual balance partial sums (Kernel.cu:199-202); memoised focal cosine
         const float area = P.obj_area[i];
-        vbx = fmaf(area, xi, vbx);
-        vby = fmaf(area, yi, vby);
-        // focal point: phi = atan2(fy - y, fx - x) - rot + PI/2 (Kernel.cu:185-188, 271-277)
-        {
-            const float ph = atan2f(h->focal_y - yi, h->focal_x - xi) - ri + h->half_pi;
-            focal += cosf(ph);
-        }
-        // own off-limit rectangle: outside the room, against every clearance
-        const float4 a = box_at(P.obj_box[i], P.obj_v0x[i], xi, yi);
+        vbx = fmaf(area, pi.x, vbx);
+        vby = fmaf(area, pi.y, vby);
+        focal += pi.w;
+        // own off-limit rectangle: outside the room, against every clearance (Kernel.cu:404-434)
+        const float4 a = box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y);
         surf += outside_room(a, h);
         {
-            float acc = 0.f;
-#pragma unroll 4
-            for (int k = 0; k < C; k++)
-                acc += overlap(a, S.CB[WS::at(k, c)]);
-            clr += acc;
-        }
-        // symmetry: reflect object i across the focal axis, best match over all j (Kernel.cu:290-314)
-        {
-            const float s = 2.0f * (fdotu - (xi * ux + yi * uy));
-            const float rx = xi + s * ux, ry = yi + s * uy;
-            float rr = tfr - ri;
-            if (rr < -pi_cmp) rr += two_pi;                    // Q18: one-sided wrap
-            float m = 0.f;
-#pragma unroll 4
-            for (int j = 0; j < n; j++) {
-                const float dx = S.X[WS::at(j, c)] - rx, dy = S.Y[WS::at(j, c)] - ry;
-                const float sd = sqrt_approx(sqrt_approx(fmaf(dx, dx, dy * dy)));   // sqrt(Distance)
-                float dt = S.Rt[WS::at(j, c)] - rr;
-                dt = dt > pi_cmp ? dt - two_pi : dt;            // Q18
-                m = fmaxf(m, fmaf(-0.4f, fabsf(dt), 5.0f - sd));
+            float acc0 = 0.f, acc1 = 0.f;
+            int k = 0;
+            for (; k + 4 <= C; k += 4) {                        // loads first, then the arithmetic
+                const float4 b0 = CBc[(k + 0) * CPW], b1 = CBc[(k + 1) * CPW], b2 = CBc[(k + 2) * CPW], b3 = CBc[(k + 3) * CPW];
+                acc0 += overlap(a, b0);
+                acc1 += overlap(a, b1);
+                acc0 += overlap(a, b2);
+                acc1 += overlap(a, b3);
             }
-            sym += m;
+            for (; k < C; k++)
+                acc0 += overlap(a, CBc[k * CPW]);
+            clr += acc0 + acc1;
+        }
+        // symmetry (Kernel.cu:290-314): reflect object i across the focal axis; the best match over
+        // all j is max_j (5 - sqrt(d) - 0.4 |dt|) = 5 - min_j (sqrt(d) + 0.4 |dt|), floored at 0.
+        // Q18: dt = rot_j - rr wraps one-sidedly (dt > PI -> dt - 2 PI); for every dt the wrapped
+        // magnitude equals min(|dt|, |dt - 2 PI|) = ||dt - PI| - PI|, two adds with |.| operand
+        // modifiers and no compare/select.  sqrt(Distance) = (d^2)^(1/4) = rsqrt(rsqrt(d^2)):
+        // MUFU.RSQ issues faster than MUFU.SQRT on sm_100 (measured).
+        {
+            const float s = 2.0f * (fdotu - (pi.x * ux + pi.y * uy));
+            const float rx = pi.x + s * ux, ry = pi.y + s * uy;
+            float rr = tfr - pi.z;
+            if (rr < -pi_cmp) rr += two_pi;                    // Q18: one-sided wrap of the reflection
+            const float rrp = rr + pi_f;                        // rot_j - rrp = dt - PI
+            float kmin = 5.0f;
+#pragma unroll kSymUnroll
+            for (int j = 0; j < n; j++) {
+                const float4 q = Pc[j * CPW];
+                const float dx = q.x - rx, dy = q.y - ry;
+                const float sd = rsqrt_approx(rsqrt_approx(fmaf(dx, dx, dy * dy)));
+                const float e = q.z - rrp;
+                const float w = fabsf(e) - pi_f;
+                kmin = fminf(kmin, fmaf(0.4f, fabsf(w), sd));
+            }
+            sym += 5.0f - kmin;
         }
         if (WITH_OFFLIMITS) {                                   // Kernel.cu:488-511, pairs i < j
             float acc = 0.f;
-            for (int j = i + 1; j < n; j++)
-                acc += overlap(a, box_at(P.obj_box[j], P.obj_v0x[j], S.X[WS::at(j, c)], S.Y[WS::at(j, c)]));
+            for (int j = i + 1; j < n; j++) {
+                const float4 q = Pc[j * CPW];
+                acc += overlap(a, box_at(P.obj_box[j], P.obj_v0x[j], q.x, q.y));
+            }
             off += acc;
         }
     }
@@ -216,24 +251,25 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
         const int4 id = P.rel_idx[r];     // distance pair (x, y) from rss[r], angle pair (z, w) from rsa[r]
         const float4 rg = P.rel_rng[r];   // 1/start, end, angleMin, angleMax
         const float4 ax = P.rel_aux[r];   // start, 1/norm, wraps
+        const float4 ps = Pc[id.x * CPW], pt = Pc[id.y * CPW];
         {
-            const float dX = S.X[WS::at(id.x, c)] - S.X[WS::at(id.y, c)];
-            const float dY = S.Y[WS::at(id.x, c)] - S.Y[WS::at(id.y, c)];
-            const float d = sqrtf(fmaf(dX, dX, dY * dY));
+            const float dX = ps.x - pt.x, dY = ps.y - pt.y;
+            const float d2 = fmaf(dX, dX, dY * dY);
+            const float d = sqrt_approx(d2);
             if (d < ax.x) {                                     // too close (Kernel.cu:219-223)
                 const float f = d * rg.x;
                 pw = fmaf(f, f, pw);
             } else if (d > rg.y) {                              // too far (Kernel.cu:225-229)
-                const float f = rg.y / d;
+                const float f = rg.y * rsqrt_approx(d2);
                 pw = fmaf(f, f, pw);
             }
         }
-        const float dX = S.X[WS::at(id.z, c)] - S.X[WS::at(id.w, c)];
-        const float dY = S.Y[WS::at(id.z, c)] - S.Y[WS::at(id.w, c)];
+        const float4 as = (id.z == id.x) ? ps : Pc[id.z * CPW], at = (id.w == id.y) ? pt : Pc[id.w * CPW];
+        const float dX = as.x - at.x, dY = as.y - at.y;
         // bearing of source seen from target, relative to the target's rotation (Kernel.cu:170-182)
         float tp = atan2f(dY, dX);
         if (tp < 0.f) tp = two_pi + tp;
-        float th = tp - S.Rt[WS::at(id.w, c)];
+        float th = tp - at.z;
         if (th < 0.f) th = two_pi + th;
         const float pen = fminf(fabsf(th - rg.z), fabsf(th - rg.w)) * ax.y;
         if (ax.z != 0.f) {                                      // range crosses zero (Kernel.cu:245-250)

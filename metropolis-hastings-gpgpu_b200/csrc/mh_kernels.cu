@@ -25,6 +25,9 @@ namespace mh {
 
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int THREADS = WARPS_PER_BLOCK * 32;
+#ifndef MH_MIN_BLOCKS
+#define MH_MIN_BLOCKS 5 // resident 128-thread blocks per SM the chain kernel is compiled for (<= 96 registers; 6 blocks = 80 registers measured slower)
+#endif
 
 struct PointRec {
     float x, y, z, rotX, rotY, rotZ;
@@ -55,15 +58,16 @@ __device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc,
         const int i = q / 3, part = q - 3 * i;
         const int src = S.perm[WS::at(i, cc)];
         float2 v;
-        if (part == 0) v = make_float2(S.X[WS::at(i, cc)], S.Y[WS::at(i, cc)]);
+        const float4 p = S.P4[WS::at(i, cc)];
+        if (part == 0) v = make_float2(p.x, p.y);
         else if (part == 1) v = make_float2(pass[src], pass[n + src]);           // z, rotX travel with swaps
-        else v = make_float2(S.Rt[WS::at(i, cc)], pass[2 * n + src]);            // rotY, rotZ
+        else v = make_float2(p.z, pass[2 * n + src]);                            // rotY, rotZ
         o2[q] = v;
     }
 }
 
 template <int G>
-__global__ void __launch_bounds__(THREADS) mh_chain_kernel(const mhLaunch L)
+__global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const mhLaunch L)
 {
     using WS = WarpState<G>;
     constexpr int CPW = WS::CPW;
@@ -89,18 +93,16 @@ __global__ void __launch_bounds__(THREADS) mh_chain_kernel(const mhLaunch L)
 
     // ---- load chain state -----------------------------------------------------------------------
     for (int i = g; i < n; i += G) {
+        float x, y, r;
         if (L.fresh) {
-            S.X[WS::at(i, c)] = cfg0[i];
-            S.Y[WS::at(i, c)] = cfg0[n + i];
-            S.Rt[WS::at(i, c)] = cfg0[2 * n + i];
+            x = cfg0[i]; y = cfg0[n + i]; r = cfg0[2 * n + i];
             S.perm[WS::at(i, c)] = (uint16_t)i;
         } else {
             const size_t o = (size_t)chain * n + i;
-            S.X[WS::at(i, c)] = L.d_x[o];
-            S.Y[WS::at(i, c)] = L.d_y[o];
-            S.Rt[WS::at(i, c)] = L.d_rot[o];
+            x = L.d_x[o]; y = L.d_y[o]; r = L.d_rot[o];
             S.perm[WS::at(i, c)] = L.d_perm[o];
         }
+        S.P4[WS::at(i, c)] = make_float4(x, y, r, focal_cos(h, x, y, r));
     }
     __syncwarp();
 
@@ -143,8 +145,8 @@ __global__ void __launch_bounds__(THREADS) mh_chain_kernel(const mhLaunch L)
         const Philox4 w = draw_block(L.seed, gchain, it, 0);
         const int p = random_int(uniform01(w.x), 2);
         int a = -1, b = -1;
-        float ax = 0.f, ay = 0.f, ar = 0.f, bx = 0.f, by = 0.f, br = 0.f;        // proposed values
-        float oax = 0.f, oay = 0.f, oar = 0.f, obx = 0.f, oby = 0.f, obr = 0.f;  // values to restore
+        float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;   // proposed state of objects a, b
+        float4 oa = na, ob = na;                                // state to restore on rejection
         if (any_free && (p != 2 || n >= 2)) {
             uint32_t redraw = 2;
             a = random_int(uniform01(w.y), n - 1);
@@ -154,34 +156,33 @@ __global__ void __launch_bounds__(THREADS) mh_chain_kernel(const mhLaunch L)
                 if (P.obj_frozen[a]) a = random_int(uniform01(rw.x), n - 1);
                 if (b >= 0 && P.obj_frozen[b]) b = random_int(uniform01(rw.y), n - 1);
             }
-            oax = S.X[WS::at(a, c)];
-            oay = S.Y[WS::at(a, c)];
-            oar = S.Rt[WS::at(a, c)];
-            ax = oax; ay = oay; ar = oar;
+            oa = S.P4[WS::at(a, c)];
+            na = oa;
             if (p == 0) {                                      // translate, sigma = W/16, H/16 (Q19), snap to the room
                 float n0, n1;
                 box_muller(w.z, w.w, n0, n1);
-                const float nx = oax + n0 * h->std_x, ny = oay + n1 * h->std_y;
-                ax = nx > room_x1 ? room_x1 : (nx < room_x0 ? room_x0 : nx);
-                ay = ny > room_y1 ? room_y1 : (ny < room_y0 ? room_y0 : ny);
+                const float nx = oa.x + n0 * h->std_x, ny = oa.y + n1 * h->std_y;
+                na.x = nx > room_x1 ? room_x1 : (nx < room_x0 ? room_x0 : nx);
+                na.y = ny > room_y1 ? room_y1 : (ny < room_y0 ? room_y0 : ny);
+                na.w = focal_cos(h, na.x, na.y, na.z);
             } else if (p == 1) {                               // rotate, one wrap into [0, 2 PI] (Kernel.cu:645-651)
                 float n0, n1;
                 box_muller(w.z, w.w, n0, n1);
-                ar = oar + n0 * h->sigma_t;
+                float ar = oa.z + n0 * h->sigma_t;
                 if (ar < 0.f) ar += h->two_pi;
                 else if (ar > h->two_pi_cmp) ar -= h->two_pi;
+                na.z = ar;
+                na.w = focal_cos(h, na.x, na.y, na.z);
             } else {                                           // swap position and rotation (Kernel.cu:675-700)
-                obx = S.X[WS::at(b, c)];
-                oby = S.Y[WS::at(b, c)];
-                obr = S.Rt[WS::at(b, c)];
-                ax = obx; ay = oby; ar = obr;
-                bx = oax; by = oay; br = oar;
+                ob = S.P4[WS::at(b, c)];
+                na = ob;                                       // the memoised cosine travels with (x, y, rot)
+                nb = oa;
             }
         }
         __syncwarp();
         if (g == 0 && a >= 0) {
-            S.X[WS::at(a, c)] = ax; S.Y[WS::at(a, c)] = ay; S.Rt[WS::at(a, c)] = ar;
-            if (b >= 0) { S.X[WS::at(b, c)] = bx; S.Y[WS::at(b, c)] = by; S.Rt[WS::at(b, c)] = br; }
+            S.P4[WS::at(a, c)] = na;
+            if (b >= 0) S.P4[WS::at(b, c)] = nb;
         }
         __syncwarp();
 
@@ -202,8 +203,8 @@ __global__ void __launch_bounds__(THREADS) mh_chain_kernel(const mhLaunch L)
                 S.perm[WS::at(b, c)] = pa;
             }
         } else if (g == 0 && a >= 0) {
-            S.X[WS::at(a, c)] = oax; S.Y[WS::at(a, c)] = oay; S.Rt[WS::at(a, c)] = oar;
-            if (b >= 0) { S.X[WS::at(b, c)] = obx; S.Y[WS::at(b, c)] = oby; S.Rt[WS::at(b, c)] = obr; }
+            S.P4[WS::at(a, c)] = oa;
+            if (b >= 0) S.P4[WS::at(b, c)] = ob;
         }
         __syncwarp();
         if (L.result_mode == 1) {
@@ -232,9 +233,10 @@ __global__ void __launch_bounds__(THREADS) mh_chain_kernel(const mhLaunch L)
     if (live) {
         for (int i = g; i < n; i += G) {
             const size_t o = (size_t)chain * n + i;
-            L.d_x[o] = S.X[WS::at(i, c)];
-            L.d_y[o] = S.Y[WS::at(i, c)];
-            L.d_rot[o] = S.Rt[WS::at(i, c)];
+            const float4 p = S.P4[WS::at(i, c)];
+            L.d_x[o] = p.x;
+            L.d_y[o] = p.y;
+            L.d_rot[o] = p.z;
             L.d_perm[o] = S.perm[WS::at(i, c)];
         }
         if (g == 0) {
@@ -270,9 +272,7 @@ __global__ void __launch_bounds__(THREADS) mh_score_kernel(const float *__restri
     const int l = live ? raw : n_layouts - 1;
     for (int i = g; i < n; i += G) {
         const PointRec pr = points[(size_t)l * n + i];
-        S.X[WS::at(i, c)] = pr.x;
-        S.Y[WS::at(i, c)] = pr.y;
-        S.Rt[WS::at(i, c)] = pr.rotY;
+        S.P4[WS::at(i, c)] = make_float4(pr.x, pr.y, pr.rotY, focal_cos(P.h, pr.x, pr.y, pr.rotY));
     }
     __syncwarp();
     RawTerms t;
