@@ -94,12 +94,15 @@ def cpu_baseline(room, target_seconds=12.0):
     OpenMP thread on all host cores, on a bounded sample of the same workload."""
     from oracle_lib import Oracle
     o = Oracle()
-    threads = int(o.lib.oracle_max_threads())
+    try:                                       # torchrun pins OMP_NUM_THREADS=1: ask for the real core count
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
     chains = threads * 4
-    _, _, secs, th = o.run(room, chains, 20, seed=1, timed=True)          # calibrate
+    _, _, secs, th = o.run(room, chains, 20, seed=1, timed=True, threads=threads)          # calibrate
     rate = chains * 20 / max(secs, 1e-6)
     iters = max(20, int(rate * target_seconds / chains))
-    _, _, secs, th = o.run(room, chains, iters, seed=1, timed=True)
+    _, _, secs, th = o.run(room, chains, iters, seed=1, timed=True, threads=threads)
     return {"value": chains * iters / secs, "unit": UNIT, "cores": th, "kind": "port",
             "sample": f"{chains} chains x {iters} iterations of the same room ({secs:.1f} s), gcc -O2, OpenMP"}
 
