@@ -69,15 +69,13 @@ template <int G> struct WarpState {
     static constexpr int CPW = 32 / G;
     float4 *P4;     // [n][CPW] {x, y, rotY, focal cosine}
     float4 *CB;     // [C][CPW] clearance AABBs of the layout under evaluation
-    uint16_t *perm; // [n][CPW] which original object's z/rotX/rotZ sits in slot i
     __device__ __forceinline__ static int at(int j, int c) { return j * CPW + c; }
     // words of shared memory one warp needs
-    __host__ __device__ static int words(int n, int C) { return (CPW * (4 * n + 4 * C) + (CPW * n + 1) / 2 + 3) & ~3; }
+    __host__ __device__ static int words(int n, int C) { return CPW * (4 * n + 4 * C); }
     __device__ __forceinline__ void bind(float *base, int n, int C)
     {
         P4 = reinterpret_cast<float4 *>(base);
         CB = P4 + n * CPW;
-        perm = reinterpret_cast<uint16_t *>(CB + C * CPW);
     }
 };
 

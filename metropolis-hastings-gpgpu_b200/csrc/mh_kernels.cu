@@ -50,13 +50,14 @@ __device__ __forceinline__ void stage_problem(float *smem, const float *g, int w
 // Write one chain's layout as point records: every lane of the warp takes part and the 6n
 // floats of the chain leave as consecutive 8-byte stores (256 B per warp instruction).
 template <int G>
-__device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc, int n, const float *pass, PointRec *out, int lane)
+__device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc, int n, const float *pass, const uint16_t *perm,
+                                                  PointRec *out, int lane)
 {
     using WS = WarpState<G>;
     float2 *o2 = reinterpret_cast<float2 *>(out);
     for (int q = lane; q < 3 * n; q += 32) {
         const int i = q / 3, part = q - 3 * i;
-        const int src = S.perm[WS::at(i, cc)];
+        const int src = perm[i];
         float2 v;
         const float4 p = S.P4[WS::at(i, cc)];
         if (part == 0) v = make_float2(p.x, p.y);
@@ -96,11 +97,10 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
         float x, y, r;
         if (L.fresh) {
             x = cfg0[i]; y = cfg0[n + i]; r = cfg0[2 * n + i];
-            S.perm[WS::at(i, c)] = (uint16_t)i;
+            if (live) L.d_perm[(size_t)chain * n + i] = (uint16_t)i;
         } else {
             const size_t o = (size_t)chain * n + i;
             x = L.d_x[o]; y = L.d_y[o]; r = L.d_rot[o];
-            S.perm[WS::at(i, c)] = L.d_perm[o];
         }
         S.P4[WS::at(i, c)] = make_float4(x, y, r, focal_cos(h, x, y, r));
     }
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
             __syncwarp();
             for (int cc = 0; cc < CPW; cc++) {
                 const int ch = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + cc;
-                if (ch < L.n_chains) write_points_warp<G>(S, cc, n, pass, points + (size_t)ch * n, lane);
+                if (ch < L.n_chains) write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)ch * n, points + (size_t)ch * n, lane);
             }
         }
     } else {
@@ -197,10 +197,11 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
         __syncwarp();
         if (acc) {
             cur = star;
-            if (g == 0 && b >= 0) {
-                const uint16_t pa = S.perm[WS::at(a, c)];
-                S.perm[WS::at(a, c)] = S.perm[WS::at(b, c)];
-                S.perm[WS::at(b, c)] = pa;
+            if (g == 0 && b >= 0 && live) {                    // z, rotX, rotZ travel with the swap: the
+                uint16_t *pm = L.d_perm + (size_t)chain * n;    // permutation lives in global memory, touched
+                const uint16_t pa = pm[a];                      // only by accepted swaps and by the write-out
+                pm[a] = pm[b];
+                pm[b] = pa;
             }
         } else if (g == 0 && a >= 0) {
             S.P4[WS::at(a, c)] = oa;
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
                 for (int cc = 0; cc < CPW; cc++)
                     if (mask & (1u << (cc * G))) {
                         const int ch = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + cc;
-                        write_points_warp<G>(S, cc, n, pass, points + (size_t)ch * n, lane);
+                        write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)ch * n, points + (size_t)ch * n, lane);
                     }
             }
         }
@@ -237,7 +238,6 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
             L.d_x[o] = p.x;
             L.d_y[o] = p.y;
             L.d_rot[o] = p.z;
-            L.d_perm[o] = S.perm[WS::at(i, c)];
         }
         if (g == 0) {
             L.d_cur_total[chain] = cur;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
     if (L.result_mode == 0) {                                  // Kernel.cu:834-842: the final current layout
         for (int cc = 0; cc < CPW; cc++) {
             const int ch = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + cc;
-            if (ch < L.n_chains) write_points_warp<G>(S, cc, n, pass, points + (size_t)ch * n, lane);
+            if (ch < L.n_chains) write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)ch * n, points + (size_t)ch * n, lane);
         }
     }
 }

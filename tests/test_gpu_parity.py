@@ -296,3 +296,39 @@ def test_full_size_properties_config3(kernel, oracle):
     ref = oracle.costs_batch(room, lay)
     assert_costs_close(room, costs[sub], ref, skip_pair=near_jump(oracle, room, lay))
     assert costs["totalCosts"].mean() > oracle.costs(room)["totalCosts"]       # the sampler climbs
+
+
+def test_parallel_tempering_matches_oracle(kernel, oracle):
+    """Extension (no reference counterpart): ladders of 4 rungs, betas swapped between neighbours
+    every 20 iterations.  Kernel and oracle implement the same spec independently."""
+    room = S.make_config(1)
+    opts = dict(seed=13, beta_start=0.5, beta_end=8.0, tempering_rungs=4, exchange_interval=20)
+    with kernel.create(room, 8, **opts) as ctx:
+        tr = ctx.run_traced(400)
+    _, _, otr = oracle.run(room, 8, 400, trace=True, **opts)
+    ladder = np.sort(np.float32([0.5, 1.2599211, 3.1748021, 8.0]))
+    for t in (0, 19, 20, 199, 399):                       # the betas of a ladder are always a permutation of it
+        for l in range(2):
+            np.testing.assert_allclose(np.sort(tr["beta"][t, 4 * l:4 * l + 4]), ladder, rtol=1e-5)
+    assert np.array_equal(tr["beta"][:20], otr["beta"][:20])
+    assert (tr["beta"][20:] != tr["beta"][:1]).any()       # exchanges do happen
+    assert np.mean(tr["beta"] == otr["beta"]) > 0.85
+    assert np.mean(tr["accepted"] == otr["accepted"]) > 0.85
+    # populations: the coldest rung ends higher than the hottest (the sampler maximises, Q10)
+    _, ck = kernel.wrapper_ex(room, 2048, 400, **opts)
+    _, co = oracle.run(room, 2048, 400, **dict(opts, seed=14))
+    assert stats.ks_2samp(ck["totalCosts"], co["totalCosts"]).pvalue > 0.01
+
+
+def test_tempering_resume_and_sharding(kernel):
+    room = S.make_config(1)
+    opts = dict(seed=5, beta_start=0.5, beta_end=8.0, tempering_rungs=4, exchange_interval=25)
+    pa, ca = kernel.wrapper_ex(room, 16, 230, **opts)
+    with kernel.create(room, 16, **opts) as b:                # exchanges fall on the same global iterations
+        b.run(60); b.run(115); b.run(55)
+        pb, cb = b.results()
+    assert pa.tobytes() == pb.tobytes() and ca.tobytes() == cb.tobytes()
+    pc, cc = kernel.wrapper_ex(room, 8, 230, chain_offset=8, **opts)
+    assert pa[8:].tobytes() == pc.tobytes()
+    with pytest.raises(pkg.KernelError, match="tempering"):
+        kernel.wrapper_ex(room, 6, 10, **opts)
