@@ -46,7 +46,9 @@ enum {
 
 enum {
     MH_EVAL_FULL = 0, /* every proposal re-evaluates every live cost term from scratch (Kernel.cu:804) */
-    MH_EVAL_DELTA = 1 /* reserved: incremental evaluation with periodic full refresh                  */
+    MH_EVAL_DELTA = 1 /* incremental evaluation: only what the moved objects touch is recomputed, the
+                         memo is rebuilt from scratch every 128 iterations; statistically equivalent to
+                         MH_EVAL_FULL, not bit-identical (csrc/mh_delta.cuh)                            */
 };
 
 typedef struct mhOptions {

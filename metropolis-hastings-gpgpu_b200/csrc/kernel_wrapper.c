@@ -144,6 +144,8 @@ static int pack_problem(const relationshipStruct *rss, const relationshipAngleSt
     H.off_obj_frozen = w; w = align4(w + n);
     H.off_clr_v0x = w;    w = align4(w + C);
     H.off_clr_src = w;    w = align4(w + C);
+    H.off_clr_adj_off = w; w = align4(w + n + 1);
+    H.off_clr_adj = w;    w = align4(w + C);
     H.smem_words = w;
     H.off_cfg0 = w;       w = align4(w + 3 * n);
     H.off_pass = w;       w = align4(w + 3 * n);
@@ -202,6 +204,18 @@ static int pack_problem(const relationshipStruct *rss, const relationshipAngleSt
     for (int i = 0; i < C; i++) {
         rect_consts(vertices, clearances[i].point1Index, b + H.off_clr_box + 4 * i, b + H.off_clr_v0x + i);
         bi[H.off_clr_src + i] = clearances[i].SourceIndex;
+        bi[H.off_clr_adj_off + clearances[i].SourceIndex + 1]++;
+    }
+    for (int i = 0; i < n; i++) /* CSR: clearances by source object (delta evaluation) */
+        bi[H.off_clr_adj_off + i + 1] += bi[H.off_clr_adj_off + i];
+    {
+        int *fill = (int *)calloc((size_t)n, sizeof(int));
+        if (!fill) { free(b); set_err("", "out of host memory", 0); return -1; }
+        for (int i = 0; i < C; i++) {
+            const int s = clearances[i].SourceIndex;
+            bi[H.off_clr_adj + bi[H.off_clr_adj_off + s] + fill[s]++] = i;
+        }
+        free(fill);
     }
     for (int i = 0; i < R; i++) {
         /* Kernel.cu:216, 243: the r-th distance relation uses rss[r]'s pair, the r-th angle
@@ -267,7 +281,7 @@ static void leave_device(int want, int prev)
  * except shared memory -- which caps the resident warps, and throughput grows about linearly
  * with resident warps up to ~18 per SM (measured on B200).  Pick the width
  * with the best modelled throughput; MH_LANES or mhOptions.lanes_per_chain override. */
-static int choose_lanes(int n, int C, int smem_words, int n_chains, int requested)
+static int choose_lanes(int n, int C, int R, int smem_words, int n_chains, int requested, int eval_mode)
 {
     int max_block = 0, max_sm = 0, sms = 0;
     if (mhdev_device_limits(&max_block, &max_sm, &sms, NULL, NULL, NULL, NULL, 0)) {
@@ -281,7 +295,7 @@ static int choose_lanes(int n, int C, int smem_words, int n_chains, int requeste
     double best_score = -1.0;
     for (int k = 0; k < 6; k++) {
         const int G = cand[k];
-        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, G, 0);
+        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, eval_mode);
         if (bytes < 0 || bytes > max_block) continue;
         if (requested == G) return G;
         int blocks_per_sm = max_sm / (bytes + 1024);
@@ -368,9 +382,11 @@ MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationship
     if (c->device < 0) c->device = prev;
     c->n = P.h->n; c->C = P.h->C; c->R = P.h->R; c->n_chains = nChains;
     c->problem_words = P.h->total_words; c->smem_words = P.h->smem_words;
-    c->lanes = choose_lanes(c->n, c->C, c->smem_words, nChains, c->opt.lanes_per_chain);
+    if (c->opt.eval_mode != MH_EVAL_FULL && c->opt.eval_mode != MH_EVAL_DELTA) { set_err("", "unknown eval_mode", 0); goto fail; }
+    c->lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, c->opt.eval_mode);
     if (c->lanes < 0) goto fail;
-    c->score_lanes = c->lanes;
+    c->score_lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, nChains, 0, MH_EVAL_FULL);
+    if (c->score_lanes < 0) goto fail;
     c->fresh = 1;
     CU(mhdev_stream_create(&c->stream));
     c->own_stream = 1;
@@ -458,6 +474,7 @@ static int launch_segment(mhContext *c, int iterations, void *d_trace)
     L.schedule = c->opt.tempering_rungs > 1 ? MH_SCHED_PER_CHAIN : c->opt.schedule;
     L.schedule_length = c->opt.schedule_length;
     L.result_mode = c->opt.result_mode;
+    L.eval_mode = c->opt.eval_mode;
     L.beta_start = (float)c->opt.beta_start; L.beta_end = (float)c->opt.beta_end;
     L.beta_log2_ratio = log2f((float)(c->opt.beta_end / c->opt.beta_start));
     L.d_x = c->d_x; L.d_y = c->d_y; L.d_rot = c->d_rot; L.d_perm = c->d_perm; L.d_cur_total = c->d_cur;
@@ -796,7 +813,7 @@ MH_API int KernelEvalCosts(const relationshipStruct *rss, const relationshipAngl
     for (size_t i = 0; i < cn; i++) {
         pts[i].x = (float)layouts[i].x; pts[i].y = (float)layouts[i].y; pts[i].rotY = (float)layouts[i].rotY;
     }
-    const int lanes = choose_lanes(n, P.h->C, P.h->smem_words, nLayouts, 0);
+    const int lanes = choose_lanes(n, P.h->C, P.h->R, P.h->smem_words, nLayouts, 0, MH_EVAL_FULL);
     if (lanes < 0) goto fail;
     CU(mhdev_stream_create(&stream));
     CU(mhdev_malloc(&d_problem, 4 * (size_t)P.h->total_words, stream));

@@ -41,11 +41,13 @@ typedef struct mhProblemHeader {
     int32_t off_rel_idx;    /* int4[R]   {rss Source, rss Target, rsa Source, rsa Target}      */
     int32_t off_rel_rng;    /* float4[R] {1/start, end, angleMin, angleMax}                    */
     int32_t off_rel_aux;    /* float4[R] {start, 1/norm, wraps (angleMin > angleMax), 0}       */
+    int32_t off_clr_adj_off; /* int32[n+1] CSR offsets: clearances whose SourceIndex is object i   */
+    int32_t off_clr_adj;    /* int32[C]   CSR list of clearance indices                            */
     int32_t smem_words;     /* words [0, smem_words) go to shared memory                       */
     int32_t off_cfg0;       /* float[3n] x, y, rotY of the caller's layout (global only)       */
     int32_t off_pass;       /* float[3n] z, rotX, rotZ pass-through, narrowed (global only)    */
     int32_t total_words;
-    int32_t pad1, pad2;
+    int32_t pad1, pad2, pad3, pad4;
 } mhProblemHeader;
 
 enum { MH_SCHED_CONSTANT = 0, MH_SCHED_GEOMETRIC = 1, MH_SCHED_LINEAR = 2, MH_SCHED_PER_CHAIN = 3 };
@@ -67,6 +69,8 @@ typedef struct mhLaunch {
     int32_t schedule;       /* MH_SCHED_*                                                      */
     int32_t schedule_length;
     int32_t result_mode;    /* 0 final layout, 1 best layout                                   */
+    int32_t eval_mode;      /* 0 full re-evaluation per proposal, 1 delta evaluation            */
+    int32_t pad_i;
     float beta_start;
     float beta_end;
     float beta_log2_ratio;  /* log2f(beta_end/beta_start)                                      */
@@ -100,7 +104,7 @@ int mhdev_launch_bestkey(const void *d_argmax_out, uint64_t chain_offset, uint64
 /* Largest dynamic shared memory per block and SM count / clock of the current device. */
 int mhdev_device_limits(int *max_smem_per_block, int *max_smem_per_sm, int *sm_count, int *clock_khz, int *cc_major,
                         int *cc_minor, char *name, int name_len);
-int mhdev_chain_smem_bytes(int smem_words, int n, int C, int lanes, int warps_per_block);
+int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int eval_mode);
 
 /* raw runtime helpers */
 int mhdev_get_device(int *dev);

@@ -42,6 +42,8 @@ struct SmemProblem {
     const float4 *clr_box;
     const float *clr_v0x;
     const int *clr_src;
+    const int *clr_adj_off;
+    const int *clr_adj;
     const int4 *rel_idx;
     const float4 *rel_rng;
     const float4 *rel_aux;
@@ -58,6 +60,8 @@ __device__ __forceinline__ SmemProblem bind_problem(const float *base)
     P.clr_box = reinterpret_cast<const float4 *>(base + P.h->off_clr_box);
     P.clr_v0x = base + P.h->off_clr_v0x;
     P.clr_src = reinterpret_cast<const int *>(base + P.h->off_clr_src);
+    P.clr_adj_off = reinterpret_cast<const int *>(base + P.h->off_clr_adj_off);
+    P.clr_adj = reinterpret_cast<const int *>(base + P.h->off_clr_adj);
     P.rel_idx = reinterpret_cast<const int4 *>(base + P.h->off_rel_idx);
     P.rel_rng = reinterpret_cast<const float4 *>(base + P.h->off_rel_rng);
     P.rel_aux = reinterpret_cast<const float4 *>(base + P.h->off_rel_aux);
@@ -97,11 +101,23 @@ struct Costs8 {
     float total, pair, visual, focal, sym, clr, off, surf; // field order of resultCosts
 };
 
-template <int G> __device__ __forceinline__ float group_sum(float v)
+// Lane -> (chain c, lane-in-group g).  Contiguous groups (c = lane / G) make the broadcast loads of
+// the pair loops cheapest (a quarter-warp touches few distinct float4s); the delta kernel, whose
+// loads are lane-strided, uses the interleaved mapping (c = lane % CPW), for which 32 lanes read 32
+// consecutive float4s without bank conflicts.  STR selects the interleaved mapping.
+template <int G, bool STR> struct LaneMap {
+    static constexpr int CPW = 32 / G;
+    __device__ __forceinline__ static int chain(int lane) { return STR ? lane % CPW : lane / G; }
+    __device__ __forceinline__ static int lane_in_group(int lane) { return STR ? lane / CPW : lane % G; }
+    __device__ __forceinline__ static int first_lane(int c) { return STR ? c : c * G; }
+    static constexpr int xor_step = STR ? CPW : 1; // lane distance between neighbouring lanes of a group
+};
+
+template <int G, bool STR = false> __device__ __forceinline__ float group_sum(float v)
 {
 #pragma unroll
     for (int m = G / 2; m > 0; m >>= 1)
-        v += __shfl_xor_sync(0xffffffffu, v, m);
+        v += __shfl_xor_sync(0xffffffffu, v, m * LaneMap<G, STR>::xor_step);
     return v;
 }
 
@@ -159,9 +175,86 @@ __device__ __forceinline__ float focal_cos(const mhProblemHeader *h, float x, fl
     return cosf(atan2f(h->focal_y - y, h->focal_x - x) - rot + h->half_pi);
 }
 
+// Symmetry (Kernel.cu:290-314).  Object i is reflected across the focal axis; the best match over
+// all j is max_j (5 - sqrt(d) - 0.4 |dt|) = 5 - min_j key(i, j), key = sqrt(d) + 0.4 |dt|, floored at 0.
+// Q18: dt = rot_j - rr wraps one-sidedly (dt > PI -> dt - 2 PI); for every dt the wrapped magnitude
+// equals min(|dt|, |dt - 2 PI|) = ||dt - PI| - PI|, two adds with |.| operand modifiers and no
+// compare/select.  sqrt(Distance) = (d^2)^(1/4) = rsqrt(rsqrt(d^2)): MUFU.RSQ issues faster than
+// MUFU.SQRT on sm_100 (measured).
+struct RowRef {
+    float rx, ry, rrp; // reflected position; reflected rotation + PI
+};
+
+__device__ __forceinline__ RowRef sym_row(const mhProblemHeader *h, const float4 pi)
+{
+    const float s = 2.0f * (h->fdotu - (pi.x * h->ux + pi.y * h->uy));
+    RowRef r;
+    r.rx = pi.x + s * h->ux;
+    r.ry = pi.y + s * h->uy;
+    float rr = h->two_focal_rot - pi.z;
+    if (rr < -h->pi_cmp) rr += h->two_pi;                      // Q18: one-sided wrap of the reflection
+    r.rrp = rr + 0.5f * h->two_pi;                              // rot_j - rrp = dt - PI
+    return r;
+}
+
+__device__ __forceinline__ float sym_key(const RowRef &r, const float4 q, const float pi_f)
+{
+    const float dx = q.x - r.rx, dy = q.y - r.ry;
+    const float sd = rsqrt_approx(rsqrt_approx(fmaf(dx, dx, dy * dy)));
+    const float e = q.z - r.rrp;
+    const float w = fabsf(e) - pi_f;
+    return fmaf(0.4f, fabsf(w), sd);
+}
+
+// Penalties of relationship r (Kernel.cu:210-263) as positive magnitudes: pd = distance penalty of
+// rss[r]'s pair, pa = angle penalty of rsa[r]'s pair.  Pc = this chain's float4 state, stride CPW.
+template <int CPW>
+__device__ __forceinline__ void rel_pen(const SmemProblem &P, const float4 *Pc, const int r, float &pd, float &pa)
+{
+    const float two_pi = P.h->two_pi;
+    const int4 id = P.rel_idx[r];     // distance pair (x, y) from rss[r], angle pair (z, w) from rsa[r]
+    const float4 rg = P.rel_rng[r];   // 1/start, end, angleMin, angleMax
+    const float4 ax = P.rel_aux[r];   // start, 1/norm, wraps
+    const float4 ps = Pc[id.x * CPW], pt = Pc[id.y * CPW];
+    pd = 0.f;
+    pa = 0.f;
+    {
+        const float dX = ps.x - pt.x, dY = ps.y - pt.y;
+        const float d2 = fmaf(dX, dX, dY * dY);
+        const float d = sqrt_approx(d2);
+        if (d < ax.x) {                                         // too close (Kernel.cu:219-223)
+            const float f = d * rg.x;
+            pd = f * f;
+        } else if (d > rg.y) {                                  // too far (Kernel.cu:225-229)
+            const float f = rg.y * rsqrt_approx(d2);
+            pd = f * f;
+        }
+    }
+    const float4 as = (id.z == id.x) ? ps : Pc[id.z * CPW], at = (id.w == id.y) ? pt : Pc[id.w * CPW];
+    const float dX = as.x - at.x, dY = as.y - at.y;
+    // bearing of source seen from target, relative to the target's rotation (Kernel.cu:170-182)
+    float tp = atan2f(dY, dX);
+    if (tp < 0.f) tp = two_pi + tp;
+    float th = tp - at.z;
+    if (th < 0.f) th = two_pi + th;
+    const float pen = fminf(fabsf(th - rg.z), fabsf(th - rg.w)) * ax.y;
+    if (ax.z != 0.f) {                                          // range crosses zero (Kernel.cu:245-250)
+        float f = rg.z + th;
+        if (f >= two_pi) {                                      // fmodf (Q17); one subtraction covers [0, 4 PI)
+            f -= two_pi;
+            if (f >= two_pi) f = fmodf(f, two_pi);
+        } else if (f < 0.f) {
+            f = fmodf(f, two_pi);
+        }
+        if (f > rg.w) pa = pen;
+    } else if (rg.z < th || th < rg.w) {                        // Q9: almost always true
+        pa = pen;
+    }
+}
+
 // All terms of one layout.  Every lane of the warp must call this (it synchronises the warp);
 // on return every lane of a group holds the group's totals.
-template <int G, bool WITH_OFFLIMITS>
+template <int G, bool WITH_OFFLIMITS, bool STR = false>
 __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState<G> &S, const int c, const int g, RawTerms &t)
 {
     using WS = WarpState<G>;
@@ -183,8 +276,7 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
     __syncwarp();
 
     // ---- rows: one object per lane per pass ----------------------------------------------------
-    const float ux = h->ux, uy = h->uy, fdotu = h->fdotu, tfr = h->two_focal_rot;
-    const float pi_cmp = h->pi_cmp, two_pi = h->two_pi, pi_f = 0.5f * h->two_pi;
+    const float pi_f = 0.5f * h->two_pi;
     const float4 *Pc = S.P4 + c, *CBc = S.CB + c;
     for (int i = g; i < n; i += G) {
         const float4 pi = Pc[i * CPW];
@@ -210,28 +302,13 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
                 acc0 += overlap(a, CBc[k * CPW]);
             clr += acc0 + acc1;
         }
-        // symmetry (Kernel.cu:290-314): reflect object i across the focal axis; the best match over
-        // all j is max_j (5 - sqrt(d) - 0.4 |dt|) = 5 - min_j (sqrt(d) + 0.4 |dt|), floored at 0.
-        // Q18: dt = rot_j - rr wraps one-sidedly (dt > PI -> dt - 2 PI); for every dt the wrapped
-        // magnitude equals min(|dt|, |dt - 2 PI|) = ||dt - PI| - PI|, two adds with |.| operand
-        // modifiers and no compare/select.  sqrt(Distance) = (d^2)^(1/4) = rsqrt(rsqrt(d^2)):
-        // MUFU.RSQ issues faster than MUFU.SQRT on sm_100 (measured).
+        // symmetry: best match of the reflection of object i over all columns (see sym_key)
         {
-            const float s = 2.0f * (fdotu - (pi.x * ux + pi.y * uy));
-            const float rx = pi.x + s * ux, ry = pi.y + s * uy;
-            float rr = tfr - pi.z;
-            if (rr < -pi_cmp) rr += two_pi;                    // Q18: one-sided wrap of the reflection
-            const float rrp = rr + pi_f;                        // rot_j - rrp = dt - PI
+            const RowRef rr = sym_row(h, pi);
             float kmin = 5.0f;
 #pragma unroll kSymUnroll
-            for (int j = 0; j < n; j++) {
-                const float4 q = Pc[j * CPW];
-                const float dx = q.x - rx, dy = q.y - ry;
-                const float sd = rsqrt_approx(rsqrt_approx(fmaf(dx, dx, dy * dy)));
-                const float e = q.z - rrp;
-                const float w = fabsf(e) - pi_f;
-                kmin = fminf(kmin, fmaf(0.4f, fabsf(w), sd));
-            }
+            for (int j = 0; j < n; j++)
+                kmin = fminf(kmin, sym_key(rr, Pc[j * CPW], pi_f));
             sym += 5.0f - kmin;
         }
         if (WITH_OFFLIMITS) {                                   // Kernel.cu:488-511, pairs i < j
@@ -246,53 +323,21 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
 
     // ---- relationships --------------------------------------------------------------------------
     for (int r = g; r < R; r += G) {
-        const int4 id = P.rel_idx[r];     // distance pair (x, y) from rss[r], angle pair (z, w) from rsa[r]
-        const float4 rg = P.rel_rng[r];   // 1/start, end, angleMin, angleMax
-        const float4 ax = P.rel_aux[r];   // start, 1/norm, wraps
-        const float4 ps = Pc[id.x * CPW], pt = Pc[id.y * CPW];
-        {
-            const float dX = ps.x - pt.x, dY = ps.y - pt.y;
-            const float d2 = fmaf(dX, dX, dY * dY);
-            const float d = sqrt_approx(d2);
-            if (d < ax.x) {                                     // too close (Kernel.cu:219-223)
-                const float f = d * rg.x;
-                pw = fmaf(f, f, pw);
-            } else if (d > rg.y) {                              // too far (Kernel.cu:225-229)
-                const float f = rg.y * rsqrt_approx(d2);
-                pw = fmaf(f, f, pw);
-            }
-        }
-        const float4 as = (id.z == id.x) ? ps : Pc[id.z * CPW], at = (id.w == id.y) ? pt : Pc[id.w * CPW];
-        const float dX = as.x - at.x, dY = as.y - at.y;
-        // bearing of source seen from target, relative to the target's rotation (Kernel.cu:170-182)
-        float tp = atan2f(dY, dX);
-        if (tp < 0.f) tp = two_pi + tp;
-        float th = tp - at.z;
-        if (th < 0.f) th = two_pi + th;
-        const float pen = fminf(fabsf(th - rg.z), fabsf(th - rg.w)) * ax.y;
-        if (ax.z != 0.f) {                                      // range crosses zero (Kernel.cu:245-250)
-            float f = rg.z + th;
-            if (f >= two_pi) {                                  // fmodf (Q17); one subtraction covers [0, 4 PI)
-                f -= two_pi;
-                if (f >= two_pi) f = fmodf(f, two_pi);
-            } else if (f < 0.f) {
-                f = fmodf(f, two_pi);
-            }
-            if (f > rg.w) pa += pen;
-        } else if (rg.z < th || th < rg.w) {                    // Q9: almost always true
-            pa += pen;
-        }
+        float pd, pe;
+        rel_pen<CPW>(P, Pc, r, pd, pe);
+        pw += pd;
+        pa += pe;
     }
 
-    t.pw = group_sum<G>(pw);
-    t.pa = group_sum<G>(pa);
-    t.vbx = group_sum<G>(vbx);
-    t.vby = group_sum<G>(vby);
-    t.focal = group_sum<G>(focal);
-    t.sym = group_sum<G>(sym);
-    t.clr = group_sum<G>(clr);
-    t.surf = group_sum<G>(surf);
-    t.off = WITH_OFFLIMITS ? group_sum<G>(off) : 0.f;
+    t.pw = group_sum<G, STR>(pw);
+    t.pa = group_sum<G, STR>(pa);
+    t.vbx = group_sum<G, STR>(vbx);
+    t.vby = group_sum<G, STR>(vby);
+    t.focal = group_sum<G, STR>(focal);
+    t.sym = group_sum<G, STR>(sym);
+    t.clr = group_sum<G, STR>(clr);
+    t.surf = group_sum<G, STR>(surf);
+    t.off = WITH_OFFLIMITS ? group_sum<G, STR>(off) : 0.f;
 }
 
 // Costs() proper (Kernel.cu:516-550): each raw term is a float, weighted in float, and the

@@ -19,6 +19,7 @@
 
 #include "mh_abi.h"
 #include "mh_costs.cuh"
+#include "mh_delta.cuh"
 #include "philox.cuh"
 
 namespace mh {
@@ -67,10 +68,13 @@ __device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc,
     }
 }
 
-template <int G>
+// DELTA = false: every proposal re-evaluates every live cost term from scratch (the parity path,
+// Kernel.cu:804).  DELTA = true: incremental evaluation (mh_delta.cuh).
+template <int G, bool DELTA>
 __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const mhLaunch L)
 {
     using WS = WarpState<G>;
+    using DS = DeltaState<G>;
     constexpr int CPW = WS::CPW;
     extern __shared__ __align__(16) float smem[];
     const float *gprob = static_cast<const float *>(L.d_problem);
@@ -79,10 +83,19 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
     const mhProblemHeader *h = P.h;
     const int n = h->n, C = h->C;
 
+    using LM = LaneMap<G, DELTA>;                              // delta mode: interleaved groups
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = lane / G, g = lane % G;
+    const int c = LM::chain(lane), g = LM::lane_in_group(lane);
     WS S;
-    S.bind(smem + L.smem_words + warp * WS::words(n, C), n, C);
+    DS D;
+    {
+        const int per_warp = WS::words(n, C) + (DELTA ? DS::words(n, h->R) : 0);
+        float *base = smem + L.smem_words + warp * per_warp;
+        S.bind(base, n, C);
+        if (DELTA) D.bind(base + WS::words(n, C), n, h->R);
+    }
+    RunSums sums = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int sel = 0;
 
     const int chain_raw = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + c;
     const bool live = chain_raw < L.n_chains;
@@ -108,9 +121,13 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
 
     float cur, best;
     if (L.fresh) {
-        RawTerms t;
-        eval_terms<G, false>(P, S, c, g, t);
-        cur = combine(h, t).total;                            // Kernel.cu:778
+        if (DELTA) {
+            cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);
+        } else {
+            RawTerms t;
+            eval_terms<G, false, DELTA>(P, S, c, g, t);
+            cur = combine(h, t).total;                        // Kernel.cu:778
+        }
         best = cur;
         if (L.result_mode == 1) {
             __syncwarp();
@@ -122,6 +139,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
     } else {
         cur = L.d_cur_total[chain];
         best = L.d_best_total[chain];
+        if (DELTA) cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);
     }
 
     const float room_x0 = h->room_minx, room_y0 = h->room_miny, room_x1 = h->room_maxx, room_y1 = h->room_maxy;
@@ -140,6 +158,9 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
             beta = L.schedule == MH_SCHED_GEOMETRIC ? L.beta_start * exp2f(tt * L.beta_log2_ratio)
                                                     : L.beta_start + (L.beta_end - L.beta_start) * tt;
         }
+
+        if (DELTA && k > 0 && (it % (uint64_t)kRefresh) == 0)   // bound the drift of the running sums
+            cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);
 
         // -- propose (Kernel.cu:576-704): every lane of the group derives the same move -------------
         const Philox4 w = draw_block(L.seed, gchain, it, 0);
@@ -186,10 +207,19 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
         }
         __syncwarp();
 
-        // -- evaluate the proposal (Kernel.cu:804): every live term, from scratch -----------------
-        RawTerms t;
-        eval_terms<G, false>(P, S, c, g, t);
-        const float star = combine(h, t).total;
+        // -- evaluate the proposal (Kernel.cu:804): every live term, from scratch -- or, in delta
+        //    mode, only what the moved objects touch ---------------------------------------------------
+        float star;
+        RunSums star_sums = sums;
+        RelStash stash;
+        const int b_eff = (b == a) ? -1 : b;                    // a swap of an object with itself moves nothing twice
+        if (DELTA) {
+            star = delta_eval<G>(P, S, D, c, g, sel, a, b_eff, oa, ob, na, nb, sums, star_sums, stash);
+        } else {
+            RawTerms t;
+            eval_terms<G, false, DELTA>(P, S, c, g, t);
+            star = combine(h, t).total;
+        }
 
         // -- accept (Kernel.cu:706-713): u < min(1, exp(beta (star - cur))), maximises (Q10) ------
         const float u = uniform01(draw_block(L.seed, gchain, it, 1).x);
@@ -197,6 +227,11 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
         __syncwarp();
         if (acc) {
             cur = star;
+            if (DELTA) {
+                sums = star_sums;
+                sel ^= 1;
+                delta_commit<G>(P, S, D, c, g, a, b_eff, stash);
+            }
             if (g == 0 && b >= 0 && live) {                    // z, rotX, rotZ travel with the swap: the
                 uint16_t *pm = L.d_perm + (size_t)chain * n;    // permutation lives in global memory, touched
                 const uint16_t pa = pm[a];                      // only by accepted swaps and by the write-out
@@ -215,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
             const unsigned mask = __ballot_sync(0xffffffffu, improved && live);
             if (mask) {
                 for (int cc = 0; cc < CPW; cc++)
-                    if (mask & (1u << (cc * G))) {
+                    if (mask & (1u << LM::first_lane(cc))) {
                         const int ch = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + cc;
                         write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)ch * n, points + (size_t)ch * n, lane);
                     }
@@ -349,16 +384,22 @@ __global__ void mh_bestkey_kernel(const float *__restrict__ best_total, const in
     *key = (long long)(k ^ 0x8000000000000000ull);
 }
 
-template <int G> static int launch_chains_g(const mhLaunch &L)
+template <int G, bool DELTA> static int launch_chains_gd(const mhLaunch &L)
 {
     using WS = WarpState<G>;
     const int chains_per_block = WARPS_PER_BLOCK * WS::CPW;
     const int blocks = (L.n_chains + chains_per_block - 1) / chains_per_block;
-    const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)WARPS_PER_BLOCK * WS::words(L.n, L.C));
-    cudaError_t e = cudaFuncSetAttribute(mh_chain_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int per_warp = WS::words(L.n, L.C) + (DELTA ? DeltaState<G>::words(L.n, L.R) : 0);
+    const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)WARPS_PER_BLOCK * per_warp);
+    cudaError_t e = cudaFuncSetAttribute(mh_chain_kernel<G, DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    mh_chain_kernel<G><<<blocks, THREADS, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
+    mh_chain_kernel<G, DELTA><<<blocks, THREADS, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
     return (int)cudaGetLastError();
+}
+
+template <int G> static int launch_chains_g(const mhLaunch &L)
+{
+    return L.eval_mode == 1 ? launch_chains_gd<G, true>(L) : launch_chains_gd<G, false>(L);
 }
 
 template <int G>
@@ -381,20 +422,21 @@ static int launch_score_g(const void *d_problem, int smem_words, int n, int C, i
 
 extern "C" {
 
-int mhdev_chain_smem_bytes(int smem_words, int n, int C, int lanes, int warps_per_block)
+int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int eval_mode)
 {
     int w = 0;
+    const bool d = eval_mode == 1;
     switch (lanes) {
-    case 1: w = mh::WarpState<1>::words(n, C); break;
-    case 2: w = mh::WarpState<2>::words(n, C); break;
-    case 4: w = mh::WarpState<4>::words(n, C); break;
-    case 8: w = mh::WarpState<8>::words(n, C); break;
-    case 16: w = mh::WarpState<16>::words(n, C); break;
-    case 32: w = mh::WarpState<32>::words(n, C); break;
+    case 1: w = mh::WarpState<1>::words(n, C) + (d ? mh::DeltaState<1>::words(n, R) : 0); break;
+    case 2: w = mh::WarpState<2>::words(n, C) + (d ? mh::DeltaState<2>::words(n, R) : 0); break;
+    case 4: w = mh::WarpState<4>::words(n, C) + (d ? mh::DeltaState<4>::words(n, R) : 0); break;
+    case 8: w = mh::WarpState<8>::words(n, C) + (d ? mh::DeltaState<8>::words(n, R) : 0); break;
+    case 16: w = mh::WarpState<16>::words(n, C) + (d ? mh::DeltaState<16>::words(n, R) : 0); break;
+    case 32: w = mh::WarpState<32>::words(n, C) + (d ? mh::DeltaState<32>::words(n, R) : 0); break;
     default: return -1;
     }
-    if (warps_per_block <= 0) warps_per_block = mh::WARPS_PER_BLOCK;
-    return 4 * (smem_words + warps_per_block * w);
+    if (d && (n + lanes - 1) / lanes > 32) return -1; /* the per-lane row flags are one 32-bit word */
+    return 4 * (smem_words + mh::WARPS_PER_BLOCK * w);
 }
 
 int mhdev_launch_chains(const mhLaunch *l)

@@ -6,12 +6,13 @@ sys.path.insert(0, ROOT)
 pkg = importlib.import_module("metropolis-hastings-gpgpu_b200")
 cid, chains, iters = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 lanes = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+mode = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 k = pkg.Kernel()
 room = pkg.synth.make_config(cid)
-with k.create(room, chains, seed=1, lanes_per_chain=lanes) as ctx:
+with k.create(room, chains, seed=1, lanes_per_chain=lanes, eval_mode=mode) as ctx:
     ctx.run(iters); ctx.synchronize(); ms_warm, _ = ctx.stats()
     ctx.reset()
     t0 = time.time(); ctx.run(iters); ctx.synchronize(); dt = time.time() - t0
     ms0 = ms_warm if 'ms_warm' in dir() else 0.0
     ms, n = ctx.stats(); ms -= ms0
-    print(f"cfg{cid} chains={chains} iters={iters} lanes={lanes}: kernel {ms:.2f} ms, {chains*iters/(ms*1e-3):.4e} proposals/s")
+    print(f"cfg{cid} chains={chains} iters={iters} lanes={lanes} mode={mode}: kernel {ms:.2f} ms, {chains*iters/(ms*1e-3):.4e} proposals/s")

@@ -332,3 +332,63 @@ def test_tempering_resume_and_sharding(kernel):
     assert pa[8:].tobytes() == pc.tobytes()
     with pytest.raises(pkg.KernelError, match="tempering"):
         kernel.wrapper_ex(room, 6, 10, **opts)
+
+
+# ---------------------------------------------------------------------------------------------
+# delta evaluation (MH_EVAL_DELTA): statistically equivalent to full evaluation
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("cid,lanes", [(1, 1), (1, 4), (2, 2), (2, 8), (3, 4), (3, 8), (3, 32), (4, 32)])
+def test_delta_running_total_equals_fresh_evaluation(kernel, oracle, cid, lanes):
+    """The memo (row minima, relationship penalties, clearance rectangles) and the running sums
+    must describe the chain's layout: after hundreds of accepted moves the total the chain carries
+    must equal a from-scratch evaluation of the layout it returns, up to float drift."""
+    room = S.make_config(cid)
+    iters = 90 if cid == 4 else 300                       # not a multiple of the refresh interval
+    with kernel.create(room, 96, seed=3, eval_mode=1, lanes_per_chain=lanes) as ctx:
+        tr = ctx.run_traced(iters)
+        pts, costs = ctx.results()
+    carried = tr["cur_total"][-1]
+    fresh = costs["totalCosts"]
+    scale = np.abs(fresh) + sum(np.abs(costs[f]) for f in L.COST_FIELDS[1:])
+    assert np.all(np.abs(carried - fresh) <= 2e-5 * scale + 1e-3), np.abs(carried - fresh).max()
+    assert 0.02 < tr["accepted"].mean() < 0.98
+    lay = layouts_from_points(room, pts[:32])
+    assert_costs_close(room, costs[:32], oracle.costs_batch(room, lay), skip_pair=near_jump(oracle, room, lay))
+
+
+def test_delta_follows_the_full_evaluation_trajectory(kernel):
+    """Same seed, same proposals: delta and full evaluation may only part where an accept decision
+    sits within rounding of its threshold."""
+    room = S.make_config(2)
+    with kernel.create(room, 64, seed=8) as f:
+        tf = f.run_traced(400)
+    with kernel.create(room, 64, seed=8, eval_mode=1) as d:
+        td = d.run_traced(400)
+    same = [(_first_divergence(tf[:, c], td[:, c]) is None) for c in range(64)]
+    assert np.mean(same) > 0.8, np.mean(same)
+    c = int(np.argmax(same))
+    np.testing.assert_allclose(td["star_total"][:, c], tf["star_total"][:, c], rtol=1e-4, atol=1e-2)
+
+
+def test_delta_distribution_matches_oracle_ks(kernel, oracle):
+    for cid, iters in ((1, 400), (2, 300)):
+        room = S.make_config(cid)
+        _, ck = kernel.wrapper_ex(room, 4096, iters, seed=2025, eval_mode=1)
+        _, co = oracle.run(room, 4096, iters, seed=5050)
+        assert stats.ks_2samp(ck["totalCosts"], co["totalCosts"]).pvalue > 0.01, cid
+
+
+def test_delta_with_frozen_best_and_annealing(kernel, oracle):
+    room = S.make_config(2)
+    room.cfg["frozen"][[2, 9]] = 1
+    pts, _ = kernel.wrapper_ex(room, 64, 300, seed=4, eval_mode=1)
+    for i in (2, 9):
+        assert np.all(pts["x"][:, i] == np.float32(room.cfg["x"][i]))
+    room = S.make_config(2)
+    _, cf = kernel.wrapper_ex(room, 256, 300, seed=9, eval_mode=1)
+    pb, cb = kernel.wrapper_ex(room, 256, 300, seed=9, eval_mode=1, result_mode=1)
+    assert np.all(cb["totalCosts"] >= cf["totalCosts"] - 1e-2)
+    _, ca = kernel.wrapper_ex(room, 1024, 600, seed=9, eval_mode=1, beta_start=0.5, beta_end=16.0, schedule=1)
+    _, oa = oracle.run(room, 1024, 600, seed=10, beta_start=0.5, beta_end=16.0, schedule=1)
+    assert stats.ks_2samp(ca["totalCosts"], oa["totalCosts"]).pvalue > 0.01
