@@ -73,6 +73,11 @@ typedef struct mhOptions {
      * iterations neighbouring rungs exchange their betas with the usual PT acceptance. */
     int32_t tempering_rungs;
     int32_t exchange_interval;
+    /* Strided sharding (0 -> 1): local chain i has global id chain_offset + i*chain_stride.  With
+     * tempering and chain_stride = number of ranks, rank r holds every ladder's chains g with
+     * g % ranks == r, so neighbouring rungs live on different GPUs and exchange through
+     * KernelTemperingExchange (below). */
+    uint64_t chain_stride;
 } mhOptions;
 
 /* One record per chain per iteration, for trajectory tests (KernelRunTraced). */
@@ -163,6 +168,16 @@ MH_API int KernelBestKey(mhContext *ctx, void *d_key);
 MH_API void KernelDecodeBestKey(long long key, unsigned long long *globalChain, float *total);
 /* Restart every chain from the caller's layout (iteration counter back to 0). */
 MH_API int KernelReset(mhContext *ctx);
+/* Cross-GPU replica exchange (extension).  A context created with tempering_rungs > 1 and
+ * chain_stride = S > 1 runs its chains at their current betas and never exchanges by itself.
+ * Every exchange_interval iterations the caller (1) takes the device arrays of per-chain
+ * totalCosts and betas from KernelTemperingState, (2) all-gathers them over the S ranks into
+ * rank-major arrays all[rank*nChains + i] (NCCL all_gather does exactly that), and (3) hands them
+ * to KernelTemperingExchange, which decides every neighbour swap of this rank's chains from the
+ * shared Philox stream -- both members of a pair reach the same decision -- and updates the local
+ * betas.  Betas move, layouts never cross the link: 8 bytes per chain per exchange. */
+MH_API int KernelTemperingState(mhContext *ctx, void **d_totals, void **d_betas);
+MH_API int KernelTemperingExchange(mhContext *ctx, const void *d_all_totals, const void *d_all_betas);
 /* Milliseconds the device spent in the MH kernels since creation (CUDA events) and how many
  * kernels were launched. */
 MH_API int KernelStats(mhContext *ctx, double *kernel_ms, long long *launches);

@@ -17,7 +17,7 @@ _P = C.c_void_p
 
 EXPORTS = ("KernelWrapper", "KernelWrapperEx", "KernelFree", "KernelLastError", "KernelEvalCosts", "KernelCreate", "KernelRun",
            "KernelRunTraced", "KernelSynchronize", "KernelResults", "KernelDeviceResults", "KernelSetStream", "KernelBest",
-           "KernelStats", "KernelDestroy", "KernelDeviceInfo", "KernelBestKey", "KernelDecodeBestKey", "KernelReset", "KernelTrim")
+           "KernelStats", "KernelDestroy", "KernelDeviceInfo", "KernelBestKey", "KernelDecodeBestKey", "KernelReset", "KernelTrim", "KernelTemperingState", "KernelTemperingExchange")
 
 
 class KernelError(RuntimeError):
@@ -69,6 +69,8 @@ class Kernel:
             lib.KernelSetStream.argtypes = [_P, _P]
             lib.KernelBestKey.argtypes = [_P, _P]
             lib.KernelReset.argtypes = [_P]
+            lib.KernelTemperingState.argtypes = [_P, C.POINTER(_P), C.POINTER(_P)]
+            lib.KernelTemperingExchange.argtypes = [_P, _P, _P]
             lib.KernelDecodeBestKey.argtypes = [C.c_longlong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]
             lib.KernelDecodeBestKey.restype = None
             Kernel._lib = lib
@@ -216,6 +218,17 @@ class Context:
         """d_key: device address of one int64 (e.g. a torch tensor's data_ptr())."""
         if self.k.lib.KernelBestKey(self.h, _P(d_key)) != 0:
             self.k._fail("KernelBestKey")
+
+    def tempering_state(self):
+        """Device addresses of this context's per-chain totalCosts and betas (float32[n_chains])."""
+        dt, db = _P(), _P()
+        if self.k.lib.KernelTemperingState(self.h, C.byref(dt), C.byref(db)) != 0:
+            self.k._fail("KernelTemperingState")
+        return dt.value, db.value
+
+    def tempering_exchange(self, d_all_totals, d_all_betas):
+        if self.k.lib.KernelTemperingExchange(self.h, _P(d_all_totals), _P(d_all_betas)) != 0:
+            self.k._fail("KernelTemperingExchange")
 
     def reset(self):
         if self.k.lib.KernelReset(self.h) != 0:

@@ -251,7 +251,7 @@ struct mhContext {
     mhOptions opt;
     int problem_words, smem_words;
     void *d_problem;
-    float *d_x, *d_y, *d_rot, *d_cur, *d_best, *d_beta;
+    float *d_x, *d_y, *d_rot, *d_cur, *d_best, *d_beta, *d_beta_snap;
     uint16_t *d_perm;
     void *d_points, *d_costs, *d_scratch;
     void *stream;
@@ -325,7 +325,7 @@ static void ctx_free(mhContext *c)
     void *st = c->stream;
     mhdev_free(c->d_problem, st); mhdev_free(c->d_x, st); mhdev_free(c->d_y, st); mhdev_free(c->d_rot, st); mhdev_free(c->d_cur, st);
     mhdev_free(c->d_best, st); mhdev_free(c->d_beta, st); mhdev_free(c->d_perm, st); mhdev_free(c->d_points, st);
-    mhdev_free(c->d_costs, st); mhdev_free(c->d_scratch, st);
+    mhdev_free(c->d_costs, st); mhdev_free(c->d_scratch, st); mhdev_free(c->d_beta_snap, st);
     for (int i = 0; i < c->n_ev; i++) { mhdev_event_destroy(c->ev[i].e0); mhdev_event_destroy(c->ev[i].e1); }
     free(c->ev);
     if (c->own_stream) mhdev_stream_destroy(c->stream);
@@ -348,8 +348,27 @@ static void take_options(mhOptions *dst, const mhOptions *src)
         memcpy(dst, src, sz);
         dst->struct_size = (uint32_t)sizeof *dst;
     }
+    if (dst->chain_stride == 0) dst->chain_stride = 1;
     if (dst->beta_start <= 0) dst->beta_start = MH_BETA;
     if (dst->beta_end <= 0) dst->beta_end = dst->beta_start;
+}
+
+/* rung r of every ladder starts at beta_start * (beta_end/beta_start)^(r/(T-1)) */
+static int init_betas(mhContext *c)
+{
+    const int T = c->opt.tempering_rungs;
+    float *hb = (float *)malloc(4 * (size_t)c->n_chains);
+    if (!hb) return 2; /* cudaErrorMemoryAllocation */
+    const float lr = log2f((float)(c->opt.beta_end / c->opt.beta_start));
+    for (int i = 0; i < c->n_chains; i++) {
+        const int r = (int)((c->opt.chain_offset + (uint64_t)i * c->opt.chain_stride) % (uint64_t)T);
+        const float t = T > 1 ? (float)r / (float)(T - 1) : 0.f;
+        hb[i] = (float)c->opt.beta_start * exp2f(t * lr);
+    }
+    int e = mhdev_h2d(c->d_beta, hb, 4 * (size_t)c->n_chains, c->stream);
+    if (!e) e = mhdev_stream_sync(c->stream);
+    free(hb);
+    return e;
 }
 
 MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationshipAngleStruct *rsa,
@@ -370,8 +389,14 @@ MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationship
     if (!c) { set_err("", "out of host memory", 0); goto fail; }
     take_options(&c->opt, opt);
     if (c->opt.tempering_rungs > 1) {
-        if (nChains % c->opt.tempering_rungs || c->opt.chain_offset % (uint64_t)c->opt.tempering_rungs) {
+        if (c->opt.chain_stride == 1 &&
+            (nChains % c->opt.tempering_rungs || c->opt.chain_offset % (uint64_t)c->opt.tempering_rungs)) {
             set_err("", "tempering: chain_offset and nChains must be multiples of tempering_rungs", 0);
+            goto fail;
+        }
+        if (c->opt.chain_stride > 1 && (c->opt.chain_offset >= c->opt.chain_stride ||
+                                         ((uint64_t)nChains * c->opt.chain_stride) % (uint64_t)c->opt.tempering_rungs)) {
+            set_err("", "tempering: strided shards need chain_offset < chain_stride and whole ladders over all ranks", 0);
             goto fail;
         }
         if (c->opt.exchange_interval <= 0) c->opt.exchange_interval = 100;
@@ -385,7 +410,8 @@ MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationship
     if (c->opt.eval_mode != MH_EVAL_FULL && c->opt.eval_mode != MH_EVAL_DELTA) { set_err("", "unknown eval_mode", 0); goto fail; }
     c->lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, c->opt.eval_mode);
     if (c->lanes < 0) goto fail;
-    c->score_lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, nChains, 0, MH_EVAL_FULL);
+    /* a pinned lane width also pins the scoring kernel, so that sharded runs report identical bits */
+    c->score_lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, MH_EVAL_FULL);
     if (c->score_lanes < 0) goto fail;
     c->fresh = 1;
     CU(mhdev_stream_create(&c->stream));
@@ -399,26 +425,12 @@ MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationship
     CU(mhdev_malloc((void **)&c->d_cur, 4 * (size_t)nChains, c->stream));
     CU(mhdev_malloc((void **)&c->d_best, 4 * (size_t)nChains, c->stream));
     CU(mhdev_malloc((void **)&c->d_beta, 4 * (size_t)nChains, c->stream));
+    CU(mhdev_malloc((void **)&c->d_beta_snap, 4 * (size_t)nChains, c->stream));
     CU(mhdev_malloc(&c->d_points, sizeof(point) * cn, c->stream));
     CU(mhdev_malloc(&c->d_costs, sizeof(resultCosts) * (size_t)nChains, c->stream));
     CU(mhdev_malloc(&c->d_scratch, 64, c->stream));
     CU(mhdev_h2d(c->d_problem, P.blob, 4 * (size_t)c->problem_words, c->stream));
-    if (c->opt.tempering_rungs > 1) {
-        /* rung r of every ladder starts at beta_start * (beta_end/beta_start)^(r/(T-1)) */
-        const int T = c->opt.tempering_rungs;
-        float *hb = (float *)malloc(4 * (size_t)nChains);
-        if (!hb) { set_err("", "out of host memory", 0); goto fail; }
-        const float lr = log2f((float)(c->opt.beta_end / c->opt.beta_start));
-        for (int i = 0; i < nChains; i++) {
-            const int r = (int)((c->opt.chain_offset + (uint64_t)i) % (uint64_t)T);
-            const float t = T > 1 ? (float)r / (float)(T - 1) : 0.f;
-            hb[i] = (float)c->opt.beta_start * exp2f(t * lr);
-        }
-        int e = mhdev_h2d(c->d_beta, hb, 4 * (size_t)nChains, c->stream);
-        if (!e) e = mhdev_stream_sync(c->stream);
-        free(hb);
-        CU(e);
-    }
+    if (c->opt.tempering_rungs > 1) CU(init_betas(c));
     CU(mhdev_stream_sync(c->stream)); /* the blob is freed below */
     free(P.blob);
     leave_device(c->opt.device, prev);
@@ -469,7 +481,7 @@ static int launch_segment(mhContext *c, int iterations, void *d_trace)
     memset(&L, 0, sizeof L);
     L.d_problem = c->d_problem; L.problem_words = c->problem_words; L.smem_words = c->smem_words;
     L.n = c->n; L.C = c->C; L.R = c->R; L.n_chains = c->n_chains; L.lanes = c->lanes; L.fresh = c->fresh;
-    L.seed = c->opt.seed; L.chain_offset = c->opt.chain_offset; L.chain_stride = 1;
+    L.seed = c->opt.seed; L.chain_offset = c->opt.chain_offset; L.chain_stride = c->opt.chain_stride;
     L.it_begin = c->opt.iteration_offset + c->it_done; L.it_count = iterations;
     L.schedule = c->opt.tempering_rungs > 1 ? MH_SCHED_PER_CHAIN : c->opt.schedule;
     L.schedule_length = c->opt.schedule_length;
@@ -506,7 +518,16 @@ static int run_iterations(mhContext *c, int iterations, mhTraceEntry *trace)
     CU(enter_device(c->device, &prev));
     if (c->opt.schedule_length <= 0 && c->opt.schedule != MH_SCHEDULE_CONSTANT) c->opt.schedule_length = iterations;
     if (trace) CU(mhdev_malloc(&d_trace, sizeof(mhTraceEntry) * (size_t)iterations * (size_t)c->n_chains, c->stream));
-    if (c->opt.tempering_rungs > 1) {
+    if (c->opt.tempering_rungs > 1 && c->opt.chain_stride > 1) {
+        /* ladders span several contexts: the caller exchanges (KernelTemperingExchange) */
+        const uint64_t ex = (uint64_t)c->opt.exchange_interval;
+        const uint64_t git = c->opt.iteration_offset + c->it_done;
+        if ((git % ex) + (uint64_t)iterations > ex) {
+            set_err("", "tempering with chain_stride > 1: a run may not cross an exchange boundary", 0);
+            goto fail;
+        }
+        if (iterations > 0 || c->fresh) CU(launch_segment(c, iterations, d_trace));
+    } else if (c->opt.tempering_rungs > 1) {
         /* segments end on exchange boundaries; the whole ladder lives in this context */
         const uint64_t ex = (uint64_t)c->opt.exchange_interval;
         int left = iterations;
@@ -520,8 +541,11 @@ static int run_iterations(mhContext *c, int iterations, mhTraceEntry *trace)
             left -= seg;
             const uint64_t gnow = c->opt.iteration_offset + c->it_done;
             if (gnow % ex == 0) {
+                /* both members of a pair must decide on the same betas: read a snapshot */
+                CU(mhdev_d2d(c->d_beta_snap, c->d_beta, 4 * (size_t)c->n_chains, c->stream));
                 CU(mhdev_launch_exchange(c->n_chains, c->opt.chain_offset, 1, c->opt.tempering_rungs, gnow / ex, gnow - 1,
-                                         c->opt.seed, c->d_cur, c->d_beta, c->opt.chain_offset, c->d_beta, c->stream));
+                                         c->opt.seed, c->d_cur, c->d_beta_snap, c->opt.chain_offset, 1, (uint64_t)c->n_chains,
+                                         c->d_beta, c->stream));
                 c->launches++;
             }
         }
@@ -682,7 +706,44 @@ MH_API int KernelReset(mhContext *ctx)
     ctx->fresh = 1;
     ctx->it_done = 0;
     ctx->costs_dirty = 1;
+    if (ctx->opt.tempering_rungs > 1) {
+        int prev = -1, rc = -1;
+        CU(enter_device(ctx->device, &prev));
+        CU(init_betas(ctx));
+        rc = 0;
+    fail:
+        if (prev >= 0) leave_device(ctx->device, prev);
+        return rc;
+    }
     return 0;
+}
+
+MH_API int KernelTemperingState(mhContext *ctx, void **d_totals, void **d_betas)
+{
+    g_err[0] = 0;
+    if (!ctx || ctx->opt.tempering_rungs <= 1) { set_err("", "context has no tempering ladder", 0); return -1; }
+    if (d_totals) *d_totals = ctx->d_cur;
+    if (d_betas) *d_betas = ctx->d_beta;
+    return 0;
+}
+
+MH_API int KernelTemperingExchange(mhContext *ctx, const void *d_all_totals, const void *d_all_betas)
+{
+    int prev = -1, rc = -1;
+    g_err[0] = 0;
+    if (!ctx || ctx->opt.tempering_rungs <= 1 || !d_all_totals || !d_all_betas) { set_err("", "bad arguments", 0); return -1; }
+    const uint64_t ex = (uint64_t)ctx->opt.exchange_interval;
+    const uint64_t gnow = ctx->opt.iteration_offset + ctx->it_done;
+    if (gnow == 0 || gnow % ex) { set_err("", "not on an exchange boundary", 0); return -1; }
+    CU(enter_device(ctx->device, &prev));
+    CU(mhdev_launch_exchange(ctx->n_chains, ctx->opt.chain_offset, ctx->opt.chain_stride, ctx->opt.tempering_rungs, gnow / ex, gnow - 1,
+                             ctx->opt.seed, (const float *)d_all_totals, (const float *)d_all_betas, 0, ctx->opt.chain_stride,
+                             (uint64_t)ctx->n_chains, ctx->d_beta, ctx->stream));
+    ctx->launches++;
+    rc = 0;
+fail:
+    if (prev >= 0) leave_device(ctx->device, prev);
+    return rc;
 }
 
 MH_API int KernelStats(mhContext *ctx, double *kernel_ms, long long *launches)

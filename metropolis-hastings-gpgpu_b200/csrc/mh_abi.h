@@ -92,11 +92,12 @@ int mhdev_launch_chains(const mhLaunch *l);
 int mhdev_launch_score(const void *d_problem, int smem_words, int n, int C, int R, int n_layouts, int lanes,
                        const void *d_points, void *d_costs, void *stream);
 /* Replica exchange between neighbouring rungs (extension).  all_total/all_beta hold the
- * values of every chain of the ladders this context takes part in, indexed by global chain
- * id - gather_base. */
+ * values of every chain of the ladders this context takes part in; chain g sits at
+ * ((g-gather_base) % gather_stride) * gather_local + (g-gather_base) / gather_stride, i.e. rank-major
+ * after an all-gather over gather_stride ranks (gather_stride = 1: plain global order). */
 int mhdev_launch_exchange(int n_chains, uint64_t chain_offset, uint64_t chain_stride, int rungs, uint64_t epoch,
                           uint64_t it_last, uint64_t seed, const float *d_all_total, const float *d_all_beta,
-                          uint64_t gather_base, float *d_beta, void *stream);
+                          uint64_t gather_base, uint64_t gather_stride, uint64_t gather_local, float *d_beta, void *stream);
 /* arg-max of totalCosts over the context's chains: d_out = {float total, int32 chain}. */
 int mhdev_launch_argmax(const void *d_costs, int n_chains, void *d_out, void *stream);
 /* d_key (device int64) = order-preserving (totalCosts, global chain id) key of the arg-max result. */
@@ -114,6 +115,7 @@ void mhdev_free(void *p, void *stream);
 int mhdev_trim(void);                                    /* return cached blocks to the driver  */
 int mhdev_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int mhdev_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int mhdev_d2d(void *dst, const void *src, size_t bytes, void *stream);
 int mhdev_memset(void *dst, int value, size_t bytes, void *stream);
 int mhdev_stream_create(void **stream);
 void mhdev_stream_destroy(void *stream);

@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(THREADS) mh_score_kernel(const float *__restri
 // decision from the gathered totals/betas, so no communication beyond the gather is needed.
 __global__ void mh_exchange_kernel(int n_chains, uint64_t chain_offset, uint64_t chain_stride, int rungs, uint64_t epoch,
                                    uint64_t it_last, uint64_t seed, const float *__restrict__ all_total,
-                                   const float *__restrict__ all_beta, uint64_t gather_base, float *__restrict__ beta)
+                                   const float *__restrict__ all_beta, uint64_t gather_base, uint64_t gather_stride,
+                                   uint64_t gather_local, float *__restrict__ beta)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_chains) return;
@@ -334,8 +335,10 @@ __global__ void mh_exchange_kernel(int n_chains, uint64_t chain_offset, uint64_t
     if (lo_r < par || lo_r + 1 >= rungs) return;
     const uint64_t glo = gch - (uint64_t)(r - lo_r), ghi = glo + 1;
     const float u = uniform01(draw_block(seed, glo, it_last, 0xFFFFu).x);
-    const double Ea = -(double)all_total[glo - gather_base], Eb = -(double)all_total[ghi - gather_base];
-    const double ba = (double)all_beta[glo - gather_base], bb = (double)all_beta[ghi - gather_base];
+    const uint64_t ilo = ((glo - gather_base) % gather_stride) * gather_local + (glo - gather_base) / gather_stride;
+    const uint64_t ihi = ((ghi - gather_base) % gather_stride) * gather_local + (ghi - gather_base) / gather_stride;
+    const double Ea = -(double)all_total[ilo], Eb = -(double)all_total[ihi];
+    const double ba = (double)all_beta[ilo], bb = (double)all_beta[ihi];
     const float pacc = fminf(1.0f, (float)exp((ba - bb) * (Ea - Eb)));
     if (u < pacc) beta[i] = (float)(r == lo_r ? bb : ba);
 }
@@ -470,12 +473,13 @@ int mhdev_launch_score(const void *d_problem, int smem_words, int n, int C, int 
 }
 
 int mhdev_launch_exchange(int n_chains, uint64_t chain_offset, uint64_t chain_stride, int rungs, uint64_t epoch, uint64_t it_last,
-                          uint64_t seed, const float *d_all_total, const float *d_all_beta, uint64_t gather_base, float *d_beta,
-                          void *stream)
+                          uint64_t seed, const float *d_all_total, const float *d_all_beta, uint64_t gather_base,
+                          uint64_t gather_stride, uint64_t gather_local, float *d_beta, void *stream)
 {
     if (n_chains <= 0) return 0;
     mh::mh_exchange_kernel<<<(n_chains + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        n_chains, chain_offset, chain_stride, rungs, epoch, it_last, seed, d_all_total, d_all_beta, gather_base, d_beta);
+        n_chains, chain_offset, chain_stride, rungs, epoch, it_last, seed, d_all_total, d_all_beta, gather_base, gather_stride,
+        gather_local, d_beta);
     return (int)cudaGetLastError();
 }
 
@@ -581,6 +585,10 @@ int mhdev_h2d(void *dst, const void *src, size_t bytes, void *stream)
 int mhdev_d2h(void *dst, const void *src, size_t bytes, void *stream)
 {
     return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream));
+}
+int mhdev_d2d(void *dst, const void *src, size_t bytes, void *stream)
+{
+    return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
 }
 int mhdev_memset(void *dst, int value, size_t bytes, void *stream)
 {

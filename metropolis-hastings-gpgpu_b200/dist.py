@@ -64,3 +64,30 @@ def global_best(kernel, ctx, n, offset, total_chains, rank, world, device, dist=
     if dist is not None and world > 1:
         dist.broadcast(layout, src=owner)
     return g, total, layout
+
+
+def tempering_epoch(ctxs_or_ctx, iterations, device, dist=None, world=1):
+    """One exchange epoch of a ladder spread over ranks (chain_stride = world): run `iterations`
+    (= exchange_interval) MH steps, all-gather the per-chain totals and betas (8 bytes per chain),
+    let every rank decide its swaps.  `ctxs_or_ctx` is this rank's context -- or, to emulate the
+    ranks of a multi-GPU run on ONE device (tests), the list of all ranks' contexts."""
+    import torch
+    ctxs = ctxs_or_ctx if isinstance(ctxs_or_ctx, (list, tuple)) else [ctxs_or_ctx]
+    for ctx in ctxs:
+        ctx.run(iterations)
+    tots, bets = [], []
+    for ctx in ctxs:
+        dt, db = ctx.tempering_state()
+        tots.append(device_view(dt, 4 * ctx.n_chains, device).view(torch.float32))
+        bets.append(device_view(db, 4 * ctx.n_chains, device).view(torch.float32))
+    if dist is not None and world > 1:
+        assert len(ctxs) == 1
+        all_t = torch.empty(world * ctxs[0].n_chains, dtype=torch.float32, device=device)
+        all_b = torch.empty_like(all_t)
+        dist.all_gather_into_tensor(all_t, tots[0])
+        dist.all_gather_into_tensor(all_b, bets[0])
+    else:
+        all_t, all_b = torch.cat(tots), torch.cat(bets)        # rank-major, like an all-gather
+    for ctx in ctxs:
+        ctx.tempering_exchange(all_t.data_ptr(), all_b.data_ptr())
+    return all_t, all_b

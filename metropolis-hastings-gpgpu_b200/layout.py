@@ -53,8 +53,8 @@ mhOptions = _dt(
     [("struct_size", "<u4", 0), ("flags", "<u4", 4), ("seed", "<u8", 8), ("chain_offset", "<u8", 16), ("iteration_offset", "<u8", 24),
      ("beta_start", "<f8", 32), ("beta_end", "<f8", 40), ("schedule", "<i4", 48), ("schedule_length", "<i4", 52),
      ("result_mode", "<i4", 56), ("eval_mode", "<i4", 60), ("lanes_per_chain", "<i4", 64), ("device", "<i4", 68),
-     ("tempering_rungs", "<i4", 72), ("exchange_interval", "<i4", 76)],
-    80,
+     ("tempering_rungs", "<i4", 72), ("exchange_interval", "<i4", 76), ("chain_stride", "<u8", 80)],
+    88,
 )
 mhTraceEntry = _dt(
     [("move", "<i4", 0), ("obj1", "<i4", 4), ("obj2", "<i4", 8), ("accepted", "<i4", 12), ("star_total", "<f4", 16),

@@ -26,12 +26,12 @@ def _has_gpu():
 
 def test_numpy_mirrors_match_header_sizes():
     assert L.check_layout()
-    assert L.mhOptions.itemsize == 80 and L.mhTraceEntry.itemsize == 32
+    assert L.mhOptions.itemsize == 88 and L.mhTraceEntry.itemsize == 32
 
 
 def test_headers_compile_as_c_and_cpp(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "mh_kernel.h"\nint main(void){return (int)sizeof(mhOptions) - 80;}\n')
+    src.write_text('#include "mh_kernel.h"\nint main(void){return (int)sizeof(mhOptions) - 88;}\n')
     for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++11")):
         exe = tmp_path / ("t_" + cc)
         subprocess.run([cc, std, "-x", "c" if cc == "gcc" else "c++", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
@@ -55,11 +55,18 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_oracle_is_not_linked_into_the_product():
+    """Nothing under oracle/ may be included, linked or loaded by the product (comments may say the word)."""
     out = subprocess.run(["nm", "-D", pkg.lib_path()], capture_output=True, text=True, check=True).stdout
     assert "oracle" not in out
-    for f in os.listdir(os.path.join(ROOT, "metropolis-hastings-gpgpu_b200", "csrc")):
-        if f.endswith((".c", ".cu", ".cuh", ".h")):
-            assert "oracle" not in open(os.path.join(ROOT, "metropolis-hastings-gpgpu_b200", "csrc", f)).read().replace("test oracle", ""), f
+    out = subprocess.run(["ldd", pkg.lib_path()], capture_output=True, text=True, check=True).stdout
+    assert "oracle" not in out
+    pdir = os.path.join(ROOT, "metropolis-hastings-gpgpu_b200")
+    for d, _, files in os.walk(pdir):
+        for f in files:
+            if f.endswith((".c", ".cu", ".cuh", ".h", ".py")) or f == "Makefile":
+                text = open(os.path.join(d, f)).read()
+                for needle in ("oracle/", "mh_oracle", "liboracle", "oracle_lib", "ref_runner", "_ref/"):
+                    assert needle not in text, (f, needle)
 
 
 def test_bad_arguments_are_rejected_before_any_device_work():

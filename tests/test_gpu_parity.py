@@ -204,9 +204,9 @@ def test_sharded_run_equals_unsharded(kernel):
     """Chains are keyed by GLOBAL chain id: splitting a run over calls /
     GPUs must not change any chain."""
     room = S.make_config(2)
-    pa, ca = kernel.wrapper_ex(room, 96, 120, seed=77)
-    pb, cb = kernel.wrapper_ex(room, 40, 120, seed=77, chain_offset=0)
-    pc, cc = kernel.wrapper_ex(room, 56, 120, seed=77, chain_offset=40)
+    pa, ca = kernel.wrapper_ex(room, 96, 120, seed=77, lanes_per_chain=4)
+    pb, cb = kernel.wrapper_ex(room, 40, 120, seed=77, chain_offset=0, lanes_per_chain=4)
+    pc, cc = kernel.wrapper_ex(room, 56, 120, seed=77, chain_offset=40, lanes_per_chain=4)
     assert pa[:40].tobytes() == pb.tobytes() and pa[40:].tobytes() == pc.tobytes()
     assert ca[:40].tobytes() == cb.tobytes() and ca[40:].tobytes() == cc.tobytes()
 
@@ -322,7 +322,7 @@ def test_parallel_tempering_matches_oracle(kernel, oracle):
 
 def test_tempering_resume_and_sharding(kernel):
     room = S.make_config(1)
-    opts = dict(seed=5, beta_start=0.5, beta_end=8.0, tempering_rungs=4, exchange_interval=25)
+    opts = dict(seed=5, beta_start=0.5, beta_end=8.0, tempering_rungs=4, exchange_interval=25, lanes_per_chain=2)
     pa, ca = kernel.wrapper_ex(room, 16, 230, **opts)
     with kernel.create(room, 16, **opts) as b:                # exchanges fall on the same global iterations
         b.run(60); b.run(115); b.run(55)
@@ -332,6 +332,13 @@ def test_tempering_resume_and_sharding(kernel):
     assert pa[8:].tobytes() == pc.tobytes()
     with pytest.raises(pkg.KernelError, match="tempering"):
         kernel.wrapper_ex(room, 6, 10, **opts)
+    # ladders whose pairs straddle warps (3 rungs): every ladder still holds a permutation of its betas
+    o3 = dict(seed=5, beta_start=0.5, beta_end=8.0, tempering_rungs=3, exchange_interval=10)
+    with kernel.create(room, 3 * 200, **o3) as ctx:
+        tr = ctx.run_traced(95)
+    want = np.sort(np.float32([0.5, 2.0, 8.0]))
+    got = np.sort(tr["beta"][-1].reshape(200, 3), axis=1)
+    np.testing.assert_allclose(got, np.tile(want, (200, 1)), rtol=1e-5)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -392,3 +399,30 @@ def test_delta_with_frozen_best_and_annealing(kernel, oracle):
     _, ca = kernel.wrapper_ex(room, 1024, 600, seed=9, eval_mode=1, beta_start=0.5, beta_end=16.0, schedule=1)
     _, oa = oracle.run(room, 1024, 600, seed=10, beta_start=0.5, beta_end=16.0, schedule=1)
     assert stats.ks_2samp(ca["totalCosts"], oa["totalCosts"]).pvalue > 0.01
+
+
+def test_cross_gpu_tempering_equals_single_context(kernel):
+    """BASELINE config 5 logic on one device: a ladder whose rungs are spread over 2 and 4 "ranks"
+    (chain_stride = ranks, one context per rank, all-gather emulated by a concatenation) must give
+    every chain exactly what the single-context ladder gives it."""
+    import torch
+    room = S.make_config(1)
+    T, ex, total, epochs = 4, 20, 32, 6
+    # lanes pinned: the lane width fixes the order of the float reductions, and the default picks it
+    # from the per-context chain count, which differs between the sharded and the unsharded run
+    opts = dict(seed=21, beta_start=0.5, beta_end=8.0, tempering_rungs=T, exchange_interval=ex, lanes_per_chain=2)
+    pa, ca = kernel.wrapper_ex(room, total, ex * epochs, **opts)
+    for ranks in (2, 4):
+        ctxs = [kernel.create(room, total // ranks, chain_offset=r, chain_stride=ranks, **opts) for r in range(ranks)]
+        stream = torch.cuda.current_stream().cuda_stream
+        for ctx in ctxs:
+            ctx.set_stream(stream)
+        for _ in range(epochs):
+            pkg.dist.tempering_epoch(ctxs, ex, torch.device("cuda", 0))
+        for r, ctx in enumerate(ctxs):
+            p, c = ctx.results()
+            assert p.tobytes() == pa[r::ranks].tobytes(), (ranks, r)
+            assert c.tobytes() == ca[r::ranks].tobytes()
+            with pytest.raises(pkg.KernelError, match="boundary"):
+                ctx.run(ex + 1)
+            ctx.close()
