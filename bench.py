@@ -122,6 +122,112 @@ def reference_gpu(config_id, chains, iters, steps, warmup, timeout_s=300):
     return r["proposals_per_s"], chains * iters / r["dev_s"], r["wall_s"]
 
 
+def quick_rate(k, room, chains, iters, **opts):
+    """proposals/s of the chain kernel alone (CUDA events), one warm-up launch then one measured."""
+    with k.create(room, chains, seed=1, **opts) as ctx:
+        ctx.run(max(1, iters // 8))
+        ctx.synchronize()
+        ms0, _ = ctx.stats()
+        ctx.reset()
+        ctx.run(iters)
+        ctx.synchronize()
+        ms1, _ = ctx.stats()
+    return chains * iters / ((ms1 - ms0) * 1e-3)
+
+
+def other_configs(k, pkg):
+    """Kernel-only throughput on the other rooms of BASELINE.json (parity-test cases, not the
+    headline): full evaluation, and delta evaluation where it is the faster mode."""
+    out = {}
+    for cid, chains, iters in ((1, 65536, 2000), (2, 65536, 1000), (4, 16384, 60)):
+        room = pkg.synth.make_config(cid)
+        e = {"n": room.n, "chains": chains, "iterations": iters, "full_eval": quick_rate(k, room, chains, iters),
+             "flops_per_proposal_contract": room.flops_per_proposal()}
+        if cid == 4:
+            e["delta_eval"] = quick_rate(k, room, chains, 256, eval_mode=1)
+        out[f"config{cid}"] = e
+    room = pkg.synth.make_config(3)
+    out["config3_delta_eval"] = quick_rate(k, room, 65536, 512, eval_mode=1)
+    return out
+
+
+def run_tempering(args, pkg, k, room, rank, local_rank, world, device, dist):
+    """BASELINE config 5: the config-3 room under parallel tempering.  With N > 1 GPUs the rungs of
+    every ladder are spread over the ranks (chain_stride = N) and neighbours exchange betas across
+    NVLink: per epoch one all-gather of 8 bytes per chain.  Reports proposals/s and the time until
+    the global best totalCosts reaches what plain MH (beta = 2) reaches with the same budget."""
+    import torch
+    rungs = world if world > 1 else 8
+    ex = 100
+    epochs = max(1, args.iterations // ex)
+    iters = epochs * ex
+    chains = args.chains - args.chains % rungs
+    total = chains * world
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def gmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # target: plain MH at beta = 2 with the same number of proposals
+    with k.create(room, chains, seed=99, chain_offset=rank * chains) as plain:
+        plain.set_stream(stream)
+        plain.run(iters)
+        target = gmax(plain.best()[1])
+    opts = dict(seed=99, beta_start=0.25, beta_end=8.0, tempering_rungs=rungs, exchange_interval=ex)
+    if world > 1:
+        ctx = k.create(room, chains, chain_offset=rank, chain_stride=world, **opts)
+    else:
+        ctx = k.create(room, chains, **opts)
+    ctx.set_stream(stream)
+
+    def epoch():
+        if world > 1:
+            pkg.dist.tempering_epoch(ctx, ex, device, dist, world)
+        else:
+            ctx.run(ex)
+
+    for _ in range(args.warmup):
+        epoch()
+    ctx.reset()
+    barrier()
+    ms0, l0 = ctx.stats()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t0 = time.perf_counter()
+    hit, best = None, -1e30
+    for e in range(epochs):
+        epoch()
+        best = max(best, gmax(ctx.best()[1]))
+        if hit is None and best >= target:
+            torch.cuda.synchronize()
+            hit = time.perf_counter() - t0
+    barrier()
+    wall = time.perf_counter() - t0
+    ms1, l1 = ctx.stats()
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        line = {"metric": METRIC, "value": total * iters / wall, "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": args.warmup,
+                "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"config 5: config-3 room (n=50) under parallel tempering, {rungs} rungs beta 0.25..8, "
+                                       f"{chains} chains/GPU x {iters} iterations, exchange every {ex}",
+                           "parallelism": f"rungs of every ladder spread over {world} GPU(s)" if world > 1 else "whole ladders in one context"},
+                "gpu_launches": int(l1 - l0), "clocks": clocks,
+                "tempering": {"rungs": rungs, "exchange_interval": ex, "epochs": epochs,
+                              "exchange_bytes_per_epoch_per_rank": 8 * chains if world > 1 else 0,
+                              "kernel_ms": ms1 - ms0, "target_totalCosts_plain_mh_same_budget": target, "best_totalCosts": best,
+                              "time_to_target_s": hit}}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def run_reference_arm(args, room, rank):
     if rank != 0:
         return
@@ -160,12 +266,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the quick kernel-only rates of the other rooms")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     pkg = importlib.import_module("metropolis-hastings-gpgpu_b200")
+    tempering = args.config == 5
+    if tempering:
+        args.config = 3
     room = pkg.synth.make_config(args.config)
 
     if args.impl == "reference":
@@ -182,6 +292,12 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     k = pkg.Kernel()
     info = k.device_info()
+    if tempering:
+        run_tempering(args, pkg, k, room, rank, local_rank, world, device, dist)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     n = room.n
     total_chains = args.chains * world
     offset = rank * args.chains
@@ -268,6 +384,8 @@ def main():
                         "call": "KernelWrapperEx (host buffers in, malloc'd result block out)"},
                 "gpu_launches": int(l1 - l0), "roofline": roofline, "clocks": clocks,
                 "best": {"global_chain": int(best[0]), "totalCosts": float(best[1])}, "device": info["name"]}
+        if not args.no_extras:
+            line["other_configs_kernel_only"] = other_configs(k, pkg)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(room)
         if not args.no_ref_gpu:
