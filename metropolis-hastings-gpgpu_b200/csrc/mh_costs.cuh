@@ -275,10 +275,74 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
     }
     __syncwarp();
 
-    // ---- rows: one object per lane per pass ----------------------------------------------------
+    // ---- rows: two objects per lane per pass (i and i+G), so that every clearance rectangle and
+    //      every column of the symmetry scan is loaded once for two rows; a last odd row runs the
+    //      one-row form of the same code ---------------------------------------------------------------
     const float pi_f = 0.5f * h->two_pi;
     const float4 *Pc = S.P4 + c, *CBc = S.CB + c;
-    for (int i = g; i < n; i += G) {
+    int i = g;
+#ifndef MH_NO_ROW_BLOCKING
+    for (; i + G < n; i += 2 * G) {
+        const int i2 = i + G;
+        const float4 p1 = Pc[i * CPW], p2 = Pc[i2 * CPW];
+        const float ar1 = P.obj_area[i], ar2 = P.obj_area[i2];
+        vbx = fmaf(ar1, p1.x, vbx);
+        vby = fmaf(ar1, p1.y, vby);
+        vbx = fmaf(ar2, p2.x, vbx);
+        vby = fmaf(ar2, p2.y, vby);
+        focal += p1.w;
+        focal += p2.w;
+        const float4 a1 = box_at(P.obj_box[i], P.obj_v0x[i], p1.x, p1.y);
+        const float4 a2 = box_at(P.obj_box[i2], P.obj_v0x[i2], p2.x, p2.y);
+        surf += outside_room(a1, h);
+        surf += outside_room(a2, h);
+        {
+            float acc1 = 0.f, acc2 = 0.f;
+            int k = 0;
+            for (; k + 2 <= C; k += 2) {
+                const float4 b0 = CBc[(k + 0) * CPW], b1 = CBc[(k + 1) * CPW];
+                acc1 += overlap(a1, b0);
+                acc2 += overlap(a2, b0);
+                acc1 += overlap(a1, b1);
+                acc2 += overlap(a2, b1);
+            }
+            for (; k < C; k++) {
+                const float4 b0 = CBc[k * CPW];
+                acc1 += overlap(a1, b0);
+                acc2 += overlap(a2, b0);
+            }
+            clr += acc1;                                        // row order i, i+G as in the one-row form
+            clr += acc2;
+        }
+        {
+            const RowRef r1 = sym_row(h, p1), r2 = sym_row(h, p2);
+            float k1 = 5.0f, k2 = 5.0f;
+#pragma unroll 4
+            for (int j = 0; j < n; j++) {
+                const float4 q = Pc[j * CPW];
+                k1 = fminf(k1, sym_key(r1, q, pi_f));
+                k2 = fminf(k2, sym_key(r2, q, pi_f));
+            }
+            sym += 5.0f - k1;
+            sym += 5.0f - k2;
+        }
+        if (WITH_OFFLIMITS) {                                   // Kernel.cu:488-511, pairs i < j
+            float acc = 0.f;
+            for (int j = i + 1; j < n; j++) {
+                const float4 q = Pc[j * CPW];
+                acc += overlap(a1, box_at(P.obj_box[j], P.obj_v0x[j], q.x, q.y));
+            }
+            off += acc;
+            acc = 0.f;
+            for (int j = i2 + 1; j < n; j++) {
+                const float4 q = Pc[j * CPW];
+                acc += overlap(a2, box_at(P.obj_box[j], P.obj_v0x[j], q.x, q.y));
+            }
+            off += acc;
+        }
+    }
+#endif
+    for (; i < n; i += G) {
         const float4 pi = Pc[i * CPW];
         // visual balance partial sums (Kernel.cu:199-202); memoised focal cosine
         const float area = P.obj_area[i];
@@ -289,18 +353,16 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
         const float4 a = box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y);
         surf += outside_room(a, h);
         {
-            float acc0 = 0.f, acc1 = 0.f;
+            float acc0 = 0.f;
             int k = 0;
-            for (; k + 4 <= C; k += 4) {                        // loads first, then the arithmetic
-                const float4 b0 = CBc[(k + 0) * CPW], b1 = CBc[(k + 1) * CPW], b2 = CBc[(k + 2) * CPW], b3 = CBc[(k + 3) * CPW];
+            for (; k + 2 <= C; k += 2) {
+                const float4 b0 = CBc[(k + 0) * CPW], b1 = CBc[(k + 1) * CPW];
                 acc0 += overlap(a, b0);
-                acc1 += overlap(a, b1);
-                acc0 += overlap(a, b2);
-                acc1 += overlap(a, b3);
+                acc0 += overlap(a, b1);
             }
             for (; k < C; k++)
                 acc0 += overlap(a, CBc[k * CPW]);
-            clr += acc0 + acc1;
+            clr += acc0;
         }
         // symmetry: best match of the reflection of object i over all columns (see sym_key)
         {

@@ -1,9 +1,9 @@
 #!/bin/bash
-# development probe: A/B of experimental libKernel builds (MH_LIB)
+# development probe: A/B of experimental libKernel builds (MH_LIB); "base" = the product build
 for v in "$@"; do
-  for l in 4 8; do
-    echo -n "$v "; MH_LIB=$PWD/metropolis-hastings-gpgpu_b200/libKernel_$v.so python tests/prof_target.py 3 65536 200 $l
-  done
-  echo -n "$v "; MH_LIB=$PWD/metropolis-hastings-gpgpu_b200/libKernel_$v.so python tests/prof_target.py 4 16384 20 32
-  echo -n "$v "; MH_LIB=$PWD/metropolis-hastings-gpgpu_b200/libKernel_$v.so python tests/prof_target.py 2 65536 500 2
+  lib=$PWD/metropolis-hastings-gpgpu_b200/libKernel_$v.so; [ "$v" = base ] && lib=$PWD/metropolis-hastings-gpgpu_b200/libKernel.so
+  for l in 4 8; do echo -n "$v "; MH_LIB=$lib python tests/prof_target.py 3 65536 400 $l; done
+  echo -n "$v "; MH_LIB=$lib python tests/prof_target.py 4 16384 40 32
+  echo -n "$v "; MH_LIB=$lib python tests/prof_target.py 2 65536 1000 2
+  echo -n "$v "; MH_LIB=$lib python tests/prof_target.py 1 65536 2000 1
 done
