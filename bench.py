@@ -144,6 +144,7 @@ def other_configs(k, pkg):
         e = {"n": room.n, "chains": chains, "iterations": iters, "full_eval": quick_rate(k, room, chains, iters),
              "flops_per_proposal_contract": room.flops_per_proposal()}
         if cid == 4:
+            e["full_eval_plain_scan"] = quick_rate(k, room, chains, iters, eval_mode=3)
             e["delta_eval"] = quick_rate(k, room, chains, 256, eval_mode=1)
         out[f"config{cid}"] = e
     room = pkg.synth.make_config(3)

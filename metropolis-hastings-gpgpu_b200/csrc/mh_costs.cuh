@@ -170,9 +170,13 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 // cos(phi) of one object, phi = atan2(fy - y, fx - x) - rot + PI/2 (Kernel.cu:185-188, 271-277).
 // A pure function of that object's state, so it is memoised in the .w lane of its float4 and
 // recomputed only for the one or two objects a proposal moves.
+__device__ __noinline__ float focal_cos_impl(float fx, float fy, float half_pi, float x, float y, float rot)
+{
+    return cosf(atan2f(fy - y, fx - x) - rot + half_pi);
+}
 __device__ __forceinline__ float focal_cos(const mhProblemHeader *h, float x, float y, float rot)
 {
-    return cosf(atan2f(h->focal_y - y, h->focal_x - x) - rot + h->half_pi);
+    return focal_cos_impl(h->focal_x, h->focal_y, h->half_pi, x, y, rot);
 }
 
 // Symmetry (Kernel.cu:290-314).  Object i is reflected across the focal axis; the best match over
@@ -208,13 +212,17 @@ __device__ __forceinline__ float sym_key(const RowRef &r, const float4 q, const 
 
 // Penalties of relationship r (Kernel.cu:210-263) as positive magnitudes: pd = distance penalty of
 // rss[r]'s pair, pa = angle penalty of rsa[r]'s pair.  Pc = this chain's float4 state, stride CPW.
+// (not inlined: it is called from several places and its ~110 instructions would otherwise be
+// replicated, and the delta/memo kernels are bound by instruction fetch, not by issue; arguments and
+// result travel in registers)
 template <int CPW>
-__device__ __forceinline__ void rel_pen(const SmemProblem &P, const float4 *Pc, const int r, float &pd, float &pa)
+__device__ __noinline__ float2 rel_pen_impl(const int4 *rel_idx, const float4 *rel_rng, const float4 *rel_aux, const float two_pi,
+                                            const float4 *Pc, const int r)
 {
-    const float two_pi = P.h->two_pi;
-    const int4 id = P.rel_idx[r];     // distance pair (x, y) from rss[r], angle pair (z, w) from rsa[r]
-    const float4 rg = P.rel_rng[r];   // 1/start, end, angleMin, angleMax
-    const float4 ax = P.rel_aux[r];   // start, 1/norm, wraps
+    float pd, pa;
+    const int4 id = rel_idx[r];       // distance pair (x, y) from rss[r], angle pair (z, w) from rsa[r]
+    const float4 rg = rel_rng[r];     // 1/start, end, angleMin, angleMax
+    const float4 ax = rel_aux[r];     // start, 1/norm, wraps
     const float4 ps = Pc[id.x * CPW], pt = Pc[id.y * CPW];
     pd = 0.f;
     pa = 0.f;
@@ -250,11 +258,20 @@ __device__ __forceinline__ void rel_pen(const SmemProblem &P, const float4 *Pc, 
     } else if (rg.z < th || th < rg.w) {                        // Q9: almost always true
         pa = pen;
     }
+    return make_float2(pd, pa);
+}
+
+template <int CPW>
+__device__ __forceinline__ void rel_pen(const SmemProblem &P, const float4 *Pc, const int r, float &pd, float &pa)
+{
+    const float2 v = rel_pen_impl<CPW>(P.rel_idx, P.rel_rng, P.rel_aux, P.h->two_pi, Pc, r);
+    pd = v.x;
+    pa = v.y;
 }
 
 // All terms of one layout.  Every lane of the warp must call this (it synchronises the warp);
 // on return every lane of a group holds the group's totals.
-template <int G, bool WITH_OFFLIMITS, bool STR = false>
+template <int G, bool WITH_OFFLIMITS, bool STR = false, bool SKIP_SYM = false>
 __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState<G> &S, const int c, const int g, RawTerms &t)
 {
     using WS = WarpState<G>;
@@ -299,6 +316,7 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
         {
             float acc1 = 0.f, acc2 = 0.f;
             int k = 0;
+#pragma unroll 2
             for (; k + 2 <= C; k += 2) {
                 const float4 b0 = CBc[(k + 0) * CPW], b1 = CBc[(k + 1) * CPW];
                 acc1 += overlap(a1, b0);
@@ -314,7 +332,7 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
             clr += acc1;                                        // row order i, i+G as in the one-row form
             clr += acc2;
         }
-        {
+        if (!SKIP_SYM) {
             const RowRef r1 = sym_row(h, p1), r2 = sym_row(h, p2);
             float k1 = 5.0f, k2 = 5.0f;
 #pragma unroll 4
@@ -355,6 +373,7 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
         {
             float acc0 = 0.f;
             int k = 0;
+#pragma unroll 2
             for (; k + 2 <= C; k += 2) {
                 const float4 b0 = CBc[(k + 0) * CPW], b1 = CBc[(k + 1) * CPW];
                 acc0 += overlap(a, b0);
@@ -365,7 +384,7 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
             clr += acc0;
         }
         // symmetry: best match of the reflection of object i over all columns (see sym_key)
-        {
+        if (!SKIP_SYM) {
             const RowRef rr = sym_row(h, pi);
             float kmin = 5.0f;
 #pragma unroll kSymUnroll

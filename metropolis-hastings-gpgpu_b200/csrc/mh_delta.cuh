@@ -31,8 +31,9 @@ template <int G> struct DeltaState {
     float2 *KM; // [2][n][CPW] {row minimum of key, a column attaining it (int bits; -1 = none below 5)}
     float2 *PR; // [R][CPW]    {distance penalty, angle penalty} of every relationship
     int n;
-    __host__ __device__ static int words(int n, int R) { return CPW * (4 * n + 2 * R); }
-    __device__ __forceinline__ void bind(float *base, int n_, int R)
+    // with_pr = false: only the symmetry memo (MH_EVAL_MEMO)
+    __host__ __device__ static int words(int n, int R, bool with_pr = true) { return CPW * (4 * n + (with_pr ? 2 * R : 0)); }
+    __device__ __forceinline__ void bind(float *base, int n_, int /*R*/)
     {
         n = n_;
         KM = reinterpret_cast<float2 *>(base);
@@ -50,12 +51,12 @@ struct RunSums {
 // Lexicographic (key, column) minimum over the G lanes of a group.
 constexpr bool kDeltaStr = true; // the delta kernel uses the interleaved lane mapping (LaneMap<G, true>)
 
-template <int G> __device__ __forceinline__ void group_argmin(float &k, int &arg)
+template <int G, bool STR> __device__ __forceinline__ void group_argmin(float &k, int &arg)
 {
 #pragma unroll
     for (int m = G / 2; m > 0; m >>= 1) {
-        const float ok = __shfl_xor_sync(0xffffffffu, k, m * LaneMap<G, kDeltaStr>::xor_step);
-        const int oa = __shfl_xor_sync(0xffffffffu, arg, m * LaneMap<G, kDeltaStr>::xor_step);
+        const float ok = __shfl_xor_sync(0xffffffffu, k, m * LaneMap<G, STR>::xor_step);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, m * LaneMap<G, STR>::xor_step);
         if (ok < k || (ok == k && (unsigned)oa < (unsigned)arg)) {
             k = ok;
             arg = oa;
@@ -63,11 +64,11 @@ template <int G> __device__ __forceinline__ void group_argmin(float &k, int &arg
     }
 }
 
-template <int G> __device__ __forceinline__ int group_min_int(int v)
+template <int G, bool STR> __device__ __forceinline__ int group_min_int(int v)
 {
 #pragma unroll
     for (int m = G / 2; m > 0; m >>= 1)
-        v = min(v, __shfl_xor_sync(0xffffffffu, v, m * LaneMap<G, kDeltaStr>::xor_step));
+        v = min(v, __shfl_xor_sync(0xffffffffu, v, m * LaneMap<G, STR>::xor_step));
     return v;
 }
 
@@ -93,6 +94,106 @@ __device__ __forceinline__ void sym_scan(const RowRef &rr, const float4 *Pc, int
     }
 }
 
+// Build the symmetry memo of the CURRENT layout: every row scans all columns.
+template <int G>
+__device__ __forceinline__ void sym_memo_build(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, int c, int g, int sel)
+{
+    constexpr int CPW = WarpState<G>::CPW;
+    const mhProblemHeader *h = P.h;
+    const int n = h->n;
+    const float pi_f = 0.5f * h->two_pi;
+    const float4 *Pc = S.P4 + c;
+    for (int i = g; i < n; i += G) {
+        float k;
+        int arg;
+        sym_scan<CPW>(sym_row(h, Pc[i * CPW]), Pc, n, 0, 1, pi_f, k, arg);
+        D.km(sel, i, c) = make_float2(k, __int_as_float(arg));
+    }
+    __syncwarp();
+}
+
+// Symmetry term of the proposal that moved objects a and b (-1 = none) to na / nb (S.P4 already holds
+// them), from the memo of the current layout in KM[sel]; writes the proposal's memo to KM[1-sel] and
+// returns sum_i (5 - min_j key(i,j)) reduced over the group.  The row minima are EXACT (min is exact),
+// and each lane adds its rows in increasing row order, exactly as the full scan of eval_terms does, so
+// the value is bit-identical to a full evaluation.  Every lane of the warp must call this.
+template <int G, bool STR>
+__device__ __forceinline__ float sym_memo_eval(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, const int c, const int g,
+                                               const int sel, const int a, const int b, const float4 na, const float4 nb)
+{
+    constexpr int CPW = WarpState<G>::CPW;
+    const mhProblemHeader *h = P.h;
+    const int n = h->n;
+    const float pi_f = 0.5f * h->two_pi;
+    const float4 *Pc = S.P4 + c;
+    const bool mva = a >= 0, mvb = b >= 0;
+    auto inM = [&](int i) { return i == a || (mvb && i == b); };
+
+    // ---- column update of the rows that did not move ---------------------------------------------------
+    unsigned flags = 0;
+    {
+        int p = 0;
+        for (int i = g; i < n; i += G, p++) {
+            if (mva && inM(i)) continue;                        // rescanned below
+            const float2 km = D.km(sel, i, c);
+            float k = km.x;
+            int arg = __float_as_int(km.y);
+            if (mva) {
+                if (arg == a || (mvb && arg == b)) {            // the remembered best column moved
+                    flags |= 1u << p;
+                    continue;
+                }
+                const RowRef rr = sym_row(h, Pc[i * CPW]);
+                const float k1 = sym_key(rr, na, pi_f);
+                if (k1 < k) { k = k1; arg = a; }
+                if (mvb) {
+                    const float k2 = sym_key(rr, nb, pi_f);
+                    if (k2 < k) { k = k2; arg = b; }
+                }
+            }
+            D.km(1 - sel, i, c) = make_float2(k, __int_as_float(arg));
+        }
+    }
+    // ---- rows rescanned by the whole group.  The moved rows a and b share one pass over the columns;
+    //      rows whose remembered column moved are taken one per trip, each group picking its own next
+    //      row, so the warp pays for the longest group queue. -----------------------------------------------
+    if (__any_sync(0xffffffffu, mva)) {
+        const RowRef ra = sym_row(h, mva ? na : Pc[0]), rb = sym_row(h, mvb ? nb : Pc[0]);
+        float ka = 5.0f, kb2 = 5.0f;
+        int aa = -1, ab = -1;
+        for (int j = g; j < n; j += G) {
+            const float4 q = Pc[j * CPW];
+            const float k1 = sym_key(ra, q, pi_f), k2 = sym_key(rb, q, pi_f);
+            if (k1 < ka) { ka = k1; aa = j; }
+            if (k2 < kb2) { kb2 = k2; ab = j; }
+        }
+        group_argmin<G, STR>(ka, aa);
+        group_argmin<G, STR>(kb2, ab);
+        if (g == 0) {
+            if (mva) D.km(1 - sel, a, c) = make_float2(ka, __int_as_float(aa));
+            if (mvb) D.km(1 - sel, b, c) = make_float2(kb2, __int_as_float(ab));
+        }
+    }
+    for (;;) {
+        const int mine = flags ? g + (__ffs(flags) - 1) * G : 0x7fffffff;
+        const int row = group_min_int<G, STR>(mine);
+        if (!__any_sync(0xffffffffu, row != 0x7fffffff)) break;
+        const bool act = row != 0x7fffffff;
+        if (act && mine == row) flags &= flags - 1;
+        float k;
+        int arg;
+        sym_scan<CPW>(sym_row(h, Pc[(act ? row : 0) * CPW]), Pc, n, g, G, pi_f, k, arg);
+        group_argmin<G, STR>(k, arg);
+        if (act && g == 0) D.km(1 - sel, row, c) = make_float2(k, __int_as_float(arg));
+    }
+    __syncwarp();
+    // ---- the sum, in the row order of the full scan --------------------------------------------------------
+    float s = 0.f;
+    for (int i = g; i < n; i += G)
+        s += 5.0f - D.km(1 - sel, i, c).x;
+    return group_sum<G, STR>(s);
+}
+
 // Rebuild the memo and the running sums of the CURRENT layout from scratch; returns its total.
 template <int G>
 __device__ __forceinline__ float delta_rebuild(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, int c, int g, int sel,
@@ -105,14 +206,8 @@ __device__ __forceinline__ float delta_rebuild(const SmemProblem &P, const WarpS
     RawTerms t;
     eval_terms<G, false, kDeltaStr>(P, S, c, g, t); // also refreshes S.CB
     cur.pw = t.pw; cur.pa = t.pa; cur.vbx = t.vbx; cur.vby = t.vby; cur.focal = t.focal; cur.clr = t.clr; cur.surf = t.surf;
-    const float pi_f = 0.5f * h->two_pi;
     const float4 *Pc = S.P4 + c;
-    for (int i = g; i < n; i += G) {
-        float k;
-        int arg;
-        sym_scan<CPW>(sym_row(h, Pc[i * CPW]), Pc, n, 0, 1, pi_f, k, arg);
-        D.km(sel, i, c) = make_float2(k, __int_as_float(arg));
-    }
+    sym_memo_build<G>(P, S, D, c, g, sel);
     for (int r = g; r < R; r += G) {
         float pd, pa;
         rel_pen<CPW>(P, Pc, r, pd, pa);
@@ -139,7 +234,7 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
     const bool mva = a >= 0, mvb = b >= 0;
     auto inM = [&](int i) { return i == a || (mvb && i == b); };
 
-    float d_pw = 0.f, d_pa = 0.f, d_vbx = 0.f, d_vby = 0.f, d_focal = 0.f, d_clr = 0.f, d_surf = 0.f, s_sym = 0.f;
+    float d_pw = 0.f, d_pa = 0.f, d_vbx = 0.f, d_vby = 0.f, d_focal = 0.f, d_clr = 0.f, d_surf = 0.f;
 
     // ---- the moved objects' own rectangles ----------------------------------------------------------
     float4 box_oa = make_float4(0.f, 0.f, 0.f, 0.f), box_na = box_oa, box_ob = box_oa, box_nb = box_oa;
@@ -248,67 +343,8 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
     MH_REL_SLOT(stash.r3, stash.v3)
 #undef MH_REL_SLOT
 
-    // ---- symmetry: column update of the rows that did not move -------------------------------------
-    unsigned flags = 0;
-    {
-        int p = 0;
-        for (int i = g; i < n; i += G, p++) {
-            if (mva && inM(i)) continue;                        // rescanned below
-            const float2 km = D.km(sel, i, c);
-            float k = km.x;
-            int arg = __float_as_int(km.y);
-            if (mva) {
-                if (arg == a || (mvb && arg == b)) {            // the remembered best column moved
-                    flags |= 1u << p;
-                    continue;
-                }
-                const RowRef rr = sym_row(h, Pc[i * CPW]);
-                const float k1 = sym_key(rr, na, pi_f);
-                if (k1 < k) { k = k1; arg = a; }
-                if (mvb) {
-                    const float k2 = sym_key(rr, nb, pi_f);
-                    if (k2 < k) { k = k2; arg = b; }
-                }
-            }
-            D.km(1 - sel, i, c) = make_float2(k, __int_as_float(arg));
-            s_sym += 5.0f - k;
-        }
-    }
-    // ---- symmetry: rows rescanned by the whole group.  The moved rows a and b share one pass over
-    //      the columns; rows whose remembered column moved are taken one per trip, each group picking
-    //      its own next row, so the warp pays for the longest group queue. ---------------------------------
-    if (__any_sync(0xffffffffu, mva)) {
-        const RowRef ra = sym_row(h, mva ? na : Pc[0]), rb = sym_row(h, mvb ? nb : Pc[0]);
-        float ka = 5.0f, kb2 = 5.0f;
-        int aa = -1, ab = -1;
-        for (int j = g; j < n; j += G) {
-            const float4 q = Pc[j * CPW];
-            const float k1 = sym_key(ra, q, pi_f), k2 = sym_key(rb, q, pi_f);
-            if (k1 < ka) { ka = k1; aa = j; }
-            if (k2 < kb2) { kb2 = k2; ab = j; }
-        }
-        group_argmin<G>(ka, aa);
-        group_argmin<G>(kb2, ab);
-        if (g == 0) {
-            if (mva) { D.km(1 - sel, a, c) = make_float2(ka, __int_as_float(aa)); s_sym += 5.0f - ka; }
-            if (mvb) { D.km(1 - sel, b, c) = make_float2(kb2, __int_as_float(ab)); s_sym += 5.0f - kb2; }
-        }
-    }
-    for (;;) {
-        const int mine = flags ? g + (__ffs(flags) - 1) * G : 0x7fffffff;
-        const int row = group_min_int<G>(mine);
-        if (!__any_sync(0xffffffffu, row != 0x7fffffff)) break;
-        const bool act = row != 0x7fffffff;
-        if (act && mine == row) flags &= flags - 1;
-        float k;
-        int arg;
-        sym_scan<CPW>(sym_row(h, Pc[(act ? row : 0) * CPW]), Pc, n, g, G, pi_f, k, arg);
-        group_argmin<G>(k, arg);
-        if (act && g == 0) {
-            D.km(1 - sel, row, c) = make_float2(k, __int_as_float(arg));
-            s_sym += 5.0f - k;
-        }
-    }
+    // ---- symmetry: exact memo (sym_memo_eval) ---------------------------------------------------------------
+    const float sym_total = sym_memo_eval<G, kDeltaStr>(P, S, D, c, g, sel, a, b, na, nb);
 
     // ---- totals ---------------------------------------------------------------------------------------
     star.pw = cur.pw + group_sum<G, kDeltaStr>(d_pw);
@@ -320,7 +356,7 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
     star.surf = cur.surf + group_sum<G, kDeltaStr>(d_surf);
     RawTerms t;
     t.pw = star.pw; t.pa = star.pa; t.vbx = star.vbx; t.vby = star.vby; t.focal = star.focal; t.clr = star.clr; t.surf = star.surf;
-    t.sym = group_sum<G, kDeltaStr>(s_sym);
+    t.sym = sym_total;
     t.off = 0.f;
     return combine(h, t).total;
 }

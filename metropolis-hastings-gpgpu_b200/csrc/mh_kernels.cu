@@ -68,11 +68,15 @@ __device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc,
     }
 }
 
-// DELTA = false: every proposal re-evaluates every live cost term from scratch (the parity path,
-// Kernel.cu:804).  DELTA = true: incremental evaluation (mh_delta.cuh).
-template <int G, bool DELTA>
+// MODE 0: every proposal re-evaluates every live cost term from scratch (Kernel.cu:804).
+// MODE 2: the same, except that the O(n^2) symmetry term comes from an exact memo of the row minima
+//         (mh_delta.cuh: sym_memo_eval) -- bit-identical totals, a fraction of the MUFU work.
+// MODE 1: incremental evaluation of every term (mh_delta.cuh: delta_eval), statistically equivalent.
+template <int G, int MODE>
 __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const mhLaunch L)
 {
+    constexpr bool DELTA = MODE == 1;
+    constexpr bool MEMO = MODE == 2;
     using WS = WarpState<G>;
     using DS = DeltaState<G>;
     constexpr int CPW = WS::CPW;
@@ -89,10 +93,10 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
     WS S;
     DS D;
     {
-        const int per_warp = WS::words(n, C) + (DELTA ? DS::words(n, h->R) : 0);
+        const int per_warp = WS::words(n, C) + (DELTA ? DS::words(n, h->R, true) : MEMO ? DS::words(n, h->R, false) : 0);
         float *base = smem + L.smem_words + warp * per_warp;
         S.bind(base, n, C);
-        if (DELTA) D.bind(base + WS::words(n, C), n, h->R);
+        if (DELTA || MEMO) D.bind(base + WS::words(n, C), n, h->R);
     }
     RunSums sums = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int sel = 0;
@@ -127,6 +131,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
             RawTerms t;
             eval_terms<G, false, DELTA>(P, S, c, g, t);
             cur = combine(h, t).total;                        // Kernel.cu:778
+            if (MEMO) sym_memo_build<G>(P, S, D, c, g, sel);
         }
         best = cur;
         if (L.result_mode == 1) {
@@ -140,6 +145,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
         cur = L.d_cur_total[chain];
         best = L.d_best_total[chain];
         if (DELTA) cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);
+        if (MEMO) sym_memo_build<G>(P, S, D, c, g, sel);
     }
 
     const float room_x0 = h->room_minx, room_y0 = h->room_miny, room_x1 = h->room_maxx, room_y1 = h->room_maxy;
@@ -215,6 +221,11 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
         const int b_eff = (b == a) ? -1 : b;                    // a swap of an object with itself moves nothing twice
         if (DELTA) {
             star = delta_eval<G>(P, S, D, c, g, sel, a, b_eff, oa, ob, na, nb, sums, star_sums, stash);
+        } else if (MEMO) {
+            RawTerms t;
+            eval_terms<G, false, false, true>(P, S, c, g, t);   // every term but symmetry, from scratch
+            t.sym = sym_memo_eval<G, false>(P, S, D, c, g, sel, a, b_eff, na, nb);
+            star = combine(h, t).total;
         } else {
             RawTerms t;
             eval_terms<G, false, DELTA>(P, S, c, g, t);
@@ -232,6 +243,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
                 sel ^= 1;
                 delta_commit<G>(P, S, D, c, g, a, b_eff, stash);
             }
+            if (MEMO) sel ^= 1;
             if (g == 0 && b >= 0 && live) {                    // z, rotX, rotZ travel with the swap: the
                 uint16_t *pm = L.d_perm + (size_t)chain * n;    // permutation lives in global memory, touched
                 const uint16_t pa = pm[a];                      // only by accepted swaps and by the write-out
@@ -387,22 +399,26 @@ __global__ void mh_bestkey_kernel(const float *__restrict__ best_total, const in
     *key = (long long)(k ^ 0x8000000000000000ull);
 }
 
-template <int G, bool DELTA> static int launch_chains_gd(const mhLaunch &L)
+template <int G, int MODE> static int launch_chains_gm(const mhLaunch &L)
 {
     using WS = WarpState<G>;
     const int chains_per_block = WARPS_PER_BLOCK * WS::CPW;
     const int blocks = (L.n_chains + chains_per_block - 1) / chains_per_block;
-    const int per_warp = WS::words(L.n, L.C) + (DELTA ? DeltaState<G>::words(L.n, L.R) : 0);
+    const int per_warp = WS::words(L.n, L.C) + (MODE == 1 ? DeltaState<G>::words(L.n, L.R, true) : MODE == 2 ? DeltaState<G>::words(L.n, L.R, false) : 0);
     const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)WARPS_PER_BLOCK * per_warp);
-    cudaError_t e = cudaFuncSetAttribute(mh_chain_kernel<G, DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mh_chain_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    mh_chain_kernel<G, DELTA><<<blocks, THREADS, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
+    mh_chain_kernel<G, MODE><<<blocks, THREADS, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
     return (int)cudaGetLastError();
 }
 
 template <int G> static int launch_chains_g(const mhLaunch &L)
 {
-    return L.eval_mode == 1 ? launch_chains_gd<G, true>(L) : launch_chains_gd<G, false>(L);
+    switch (L.eval_mode) {
+    case 1: return launch_chains_gm<G, 1>(L);
+    case 2: return launch_chains_gm<G, 2>(L);
+    default: return launch_chains_gm<G, 0>(L);
+    }
 }
 
 template <int G>
@@ -428,17 +444,17 @@ extern "C" {
 int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int eval_mode)
 {
     int w = 0;
-    const bool d = eval_mode == 1;
+    const bool memo = eval_mode == 1 || eval_mode == 2, pr = eval_mode == 1;
     switch (lanes) {
-    case 1: w = mh::WarpState<1>::words(n, C) + (d ? mh::DeltaState<1>::words(n, R) : 0); break;
-    case 2: w = mh::WarpState<2>::words(n, C) + (d ? mh::DeltaState<2>::words(n, R) : 0); break;
-    case 4: w = mh::WarpState<4>::words(n, C) + (d ? mh::DeltaState<4>::words(n, R) : 0); break;
-    case 8: w = mh::WarpState<8>::words(n, C) + (d ? mh::DeltaState<8>::words(n, R) : 0); break;
-    case 16: w = mh::WarpState<16>::words(n, C) + (d ? mh::DeltaState<16>::words(n, R) : 0); break;
-    case 32: w = mh::WarpState<32>::words(n, C) + (d ? mh::DeltaState<32>::words(n, R) : 0); break;
+    case 1: w = mh::WarpState<1>::words(n, C) + (memo ? mh::DeltaState<1>::words(n, R, pr) : 0); break;
+    case 2: w = mh::WarpState<2>::words(n, C) + (memo ? mh::DeltaState<2>::words(n, R, pr) : 0); break;
+    case 4: w = mh::WarpState<4>::words(n, C) + (memo ? mh::DeltaState<4>::words(n, R, pr) : 0); break;
+    case 8: w = mh::WarpState<8>::words(n, C) + (memo ? mh::DeltaState<8>::words(n, R, pr) : 0); break;
+    case 16: w = mh::WarpState<16>::words(n, C) + (memo ? mh::DeltaState<16>::words(n, R, pr) : 0); break;
+    case 32: w = mh::WarpState<32>::words(n, C) + (memo ? mh::DeltaState<32>::words(n, R, pr) : 0); break;
     default: return -1;
     }
-    if (d && (n + lanes - 1) / lanes > 32) return -1; /* the per-lane row flags are one 32-bit word */
+    if (memo && (n + lanes - 1) / lanes > 32) return -1; /* the per-lane row flags are one 32-bit word */
     return 4 * (smem_words + mh::WARPS_PER_BLOCK * w);
 }
 

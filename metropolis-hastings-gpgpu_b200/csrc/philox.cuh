@@ -22,7 +22,7 @@ struct Philox4 {
     uint32_t x, y, z, w;
 };
 
-__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+__device__ __noinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
@@ -50,7 +50,7 @@ __device__ __forceinline__ Philox4 draw_block(uint64_t seed, uint64_t chain, uin
 __device__ __forceinline__ float uniform01(uint32_t x) { return __fmaf_rn((float)x, 0x1p-32f, 0x1p-33f); }
 
 // curand_normal.h:70-92: first normal = s sin v, second = s cos v.
-__device__ __forceinline__ void box_muller(uint32_t x, uint32_t y, float &n0, float &n1)
+__device__ __noinline__ float2 box_muller_pair(uint32_t x, uint32_t y)
 {
     const float k = 1.46291807e-09f; // 2 pi / 2^32
     const float u = uniform01(x);
@@ -58,8 +58,13 @@ __device__ __forceinline__ void box_muller(uint32_t x, uint32_t y, float &n0, fl
     const float s = sqrtf(-2.0f * logf(u));
     float sn, cs;
     sincosf(v, &sn, &cs);
-    n0 = s * sn;
-    n1 = s * cs;
+    return make_float2(s * sn, s * cs);
+}
+__device__ __forceinline__ void box_muller(uint32_t x, uint32_t y, float &n0, float &n1)
+{
+    const float2 p = box_muller_pair(x, y);
+    n0 = p.x;
+    n1 = p.y;
 }
 
 // Kernel.cu:566-574 with u supplied: trunc(u * (max - min + 0.999999) + min), the scale in

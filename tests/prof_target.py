@@ -4,11 +4,13 @@ import importlib, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("metropolis-hastings-gpgpu_b200")
-cid, chains, iters = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+spec = sys.argv[1]
+cid = int(spec) if spec.isdigit() else spec
+chains, iters = int(sys.argv[2]), int(sys.argv[3])
 lanes = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 mode = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 k = pkg.Kernel()
-room = pkg.synth.make_config(cid)
+room = pkg.synth.make_config(cid) if isinstance(cid, int) else pkg.synth.make_room(*[int(v) for v in cid.split(',')], 12.0, 9.0, 4242)  # custom 'n,C,R'
 with k.create(room, chains, seed=1, lanes_per_chain=lanes, eval_mode=mode) as ctx:
     ctx.run(iters); ctx.synchronize(); ms_warm, _ = ctx.stats()
     ctx.reset()

@@ -426,3 +426,43 @@ def test_cross_gpu_tempering_equals_single_context(kernel):
             with pytest.raises(pkg.KernelError, match="boundary"):
                 ctx.run(ex + 1)
             ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# exact symmetry memo (MH_EVAL_MEMO): bit-identical to the full scan
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("cid,lanes,chains,iters", [(1, 1, 64, 600), (1, 4, 64, 600), (2, 2, 96, 500), (2, 8, 96, 500),
+                                                     (3, 4, 64, 300), (3, 8, 64, 300), (3, 32, 32, 300), (4, 32, 16, 60)])
+def test_memo_mode_is_bit_identical_to_full_scan(kernel, cid, lanes, chains, iters):
+    """The symmetry memo keeps exact row minima and sums them in the order of the full scan, so every
+    proposal's total, every accept decision and every returned bit must equal MH_EVAL_FULL."""
+    room = S.make_config(cid)
+    out = []
+    for mode in (3, 2):                                       # 3 = the plain n^2 scan, forced
+        with kernel.create(room, chains, seed=17, lanes_per_chain=lanes, eval_mode=mode, result_mode=cid % 2) as ctx:
+            tr = ctx.run_traced(iters)
+            ctx.run(37)                                        # and across a second launch (memo rebuilt)
+            p, c = ctx.results()
+        out.append((tr, p, c))
+    (t0, p0, c0), (t2, p2, c2) = out
+    assert t0.tobytes() == t2.tobytes()
+    assert p0.tobytes() == p2.tobytes() and c0.tobytes() == c2.tobytes()
+    assert 0.02 < t0["accepted"].mean() < 0.98
+
+
+def test_default_mode_switches_to_the_memo_transparently(kernel):
+    """MH_EVAL_FULL uses the memo form from 64 objects up; callers must not be able to tell."""
+    room = S.make_room(70, 30, 40, 10.0, 8.0, 99)
+    pa, ca = kernel.wrapper_ex(room, 48, 150, seed=3, lanes_per_chain=8, eval_mode=0)
+    pb, cb = kernel.wrapper_ex(room, 48, 150, seed=3, lanes_per_chain=8, eval_mode=3)
+    assert pa.tobytes() == pb.tobytes() and ca.tobytes() == cb.tobytes()
+
+
+def test_memo_mode_with_frozen_swaps_and_tempering(kernel):
+    room = S.make_config(2)
+    room.cfg["frozen"][[0, 7, 8]] = 1
+    opts = dict(seed=23, beta_start=0.5, beta_end=8.0, tempering_rungs=4, exchange_interval=25, lanes_per_chain=4)
+    pa, ca = kernel.wrapper_ex(room, 64, 260, eval_mode=3, **opts)
+    pb, cb = kernel.wrapper_ex(room, 64, 260, eval_mode=2, **opts)
+    assert pa.tobytes() == pb.tobytes() and ca.tobytes() == cb.tobytes()
