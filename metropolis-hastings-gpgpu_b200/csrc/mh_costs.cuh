@@ -299,7 +299,7 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
     const float4 *Pc = S.P4 + c, *CBc = S.CB + c;
     int i = g;
 #ifndef MH_NO_ROW_BLOCKING
-    for (; i + G < n; i += 2 * G) {
+    for (; !SKIP_SYM && i + G < n; i += 2 * G) {      // (the memo form has no column scan to share: one-row code only)
         const int i2 = i + G;
         const float4 p1 = Pc[i * CPW], p2 = Pc[i2 * CPW];
         const float ar1 = P.obj_area[i], ar2 = P.obj_area[i2];

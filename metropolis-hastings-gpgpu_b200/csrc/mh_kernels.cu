@@ -26,6 +26,9 @@ namespace mh {
 
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int THREADS = WARPS_PER_BLOCK * 32;
+#ifndef MH_MEMO_MIN_BLOCKS
+#define MH_MEMO_MIN_BLOCKS 5 // same for the memo / delta forms
+#endif
 #ifndef MH_MIN_BLOCKS
 #define MH_MIN_BLOCKS 5 // resident 128-thread blocks per SM the chain kernel is compiled for (<= 96 registers; 6 blocks = 80 registers measured slower)
 #endif
@@ -50,6 +53,12 @@ __device__ __forceinline__ void stage_problem(float *smem, const float *g, int w
 
 // Write one chain's layout as point records: every lane of the warp takes part and the 6n
 // floats of the chain leave as consecutive 8-byte stores (256 B per warp instruction).
+// Kernel.cu:706-713: u < min(1, exp(beta (star - cur))), the exponential in double like the reference.
+__device__ __forceinline__ bool accept_move(float u, float beta, float star, float cur)
+{
+    return u < fminf(1.0f, (float)exp((double)beta * ((double)star - (double)cur)));
+}
+
 template <int G>
 __device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc, int n, const float *pass, const uint16_t *perm,
                                                   PointRec *out, int lane)
@@ -73,7 +82,7 @@ __device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc,
 //         (mh_delta.cuh: sym_memo_eval) -- bit-identical totals, a fraction of the MUFU work.
 // MODE 1: incremental evaluation of every term (mh_delta.cuh: delta_eval), statistically equivalent.
 template <int G, int MODE>
-__global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const mhLaunch L)
+__global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_MIN_BLOCKS) mh_chain_kernel(const mhLaunch L)
 {
     constexpr bool DELTA = MODE == 1;
     constexpr bool MEMO = MODE == 2;
@@ -234,7 +243,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
 
         // -- accept (Kernel.cu:706-713): u < min(1, exp(beta (star - cur))), maximises (Q10) ------
         const float u = uniform01(draw_block(L.seed, gchain, it, 1).x);
-        const bool acc = u < fminf(1.0f, (float)exp((double)beta * ((double)star - (double)cur)));
+        const bool acc = accept_move(u, beta, star, cur);
         __syncwarp();
         if (acc) {
             cur = star;

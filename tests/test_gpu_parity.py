@@ -466,3 +466,54 @@ def test_memo_mode_with_frozen_swaps_and_tempering(kernel):
     pa, ca = kernel.wrapper_ex(room, 64, 260, eval_mode=3, **opts)
     pb, cb = kernel.wrapper_ex(room, 64, 260, eval_mode=2, **opts)
     assert pa.tobytes() == pb.tobytes() and ca.tobytes() == cb.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------
+# robustness
+# ---------------------------------------------------------------------------------------------
+
+def test_large_rooms_and_the_shared_memory_limit(kernel, oracle):
+    room = S.make_room(300, 120, 150, 30.0, 20.0, 5)            # 10 rows per lane at 32 lanes
+    lay = S.random_layouts(room, 8, 2)
+    got = kernel.eval_costs(room, lay)
+    assert_costs_close(room, got, oracle.costs_batch(room, lay), skip_pair=near_jump(oracle, room, lay))
+    pts, costs = kernel.wrapper_ex(room, 40, 30, seed=1)
+    lay = layouts_from_points(room, pts[:6])
+    assert_costs_close(room, costs[:6], oracle.costs_batch(room, lay), skip_pair=near_jump(oracle, room, lay))
+    too_big = S.make_room(4000, 100, 100, 60.0, 60.0, 6)
+    with pytest.raises(pkg.KernelError, match="shared memory"):
+        kernel.wrapper_ex(too_big, 4, 2, seed=1)
+
+
+def test_concurrent_callers(kernel):
+    """The library must be callable from several threads at once (the reference's wrapper is not:
+    it synchronises the whole device); every thread must get exactly what a lone call gets."""
+    import threading
+    room = S.make_config(2)
+    want = kernel.wrapper_ex(room, 256, 200, seed=11, lanes_per_chain=2)
+    got, errs = [None] * 6, []
+
+    def work(i):
+        try:
+            got[i] = kernel.wrapper_ex(room, 256, 200, seed=11, lanes_per_chain=2)
+        except Exception as e:                                   # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    for p, c in got:
+        assert p.tobytes() == want[0].tobytes() and c.tobytes() == want[1].tobytes()
+
+
+def test_reference_entry_point_uses_a_fresh_seed_per_call(kernel, monkeypatch):
+    room = S.make_config(1)
+    monkeypatch.delenv("MH_SEED", raising=False)
+    a, _ = kernel.wrapper(room, 32, 100)
+    b, _ = kernel.wrapper(room, 32, 100)
+    assert a.tobytes() != b.tobytes()                           # Kernel.cu:943 seeds with the clock
+    monkeypatch.setenv("MH_SEED", "42")
+    c, _ = kernel.wrapper(room, 32, 100)
+    d, _ = kernel.wrapper(room, 32, 100)
+    assert c.tobytes() == d.tobytes()
