@@ -23,6 +23,11 @@
 #include "../../include/mh_kernel.h"
 #include "mh_abi.h"
 
+#if defined(__linux__)
+#include <sys/mman.h>
+#include <unistd.h>
+#endif
+
 #define MH_TLS __thread
 #define MH_MEMO_MIN_OBJS 64 /* nObjs from which MH_EVAL_FULL runs as the exact symmetry memo */
 #define MH_MAX_BLOCKS_PER_SM 5 /* 128-thread blocks at the chain kernel's register cap (MH_MIN_BLOCKS in mh_kernels.cu) */
@@ -332,6 +337,22 @@ static void ctx_free(mhContext *c)
     free(c->ev);
     if (c->own_stream) mhdev_stream_destroy(c->stream);
     free(c);
+}
+
+/* The result block must come from plain malloc() (the reference's callers free() it, Kernel.cu:928),
+ * so it cannot be pinned memory.  A fresh 80 MB malloc is untouched address space: copying into it
+ * page-faults 20 000 times.  Populate it in one call first (Linux >= 5.14; harmless if unsupported). */
+static void prefault(void *p, size_t bytes)
+{
+#if defined(__linux__) && defined(MADV_POPULATE_WRITE)
+    if (bytes >= (1u << 20)) {
+        const uintptr_t page = (uintptr_t)sysconf(_SC_PAGESIZE);
+        const uintptr_t a = ((uintptr_t)p + page - 1) & ~(page - 1), e = ((uintptr_t)p + bytes) & ~(page - 1);
+        if (e > a) (void)madvise((void *)a, (size_t)(e - a), MADV_POPULATE_WRITE);
+    }
+#else
+    (void)p; (void)bytes;
+#endif
 }
 
 static void default_options(mhOptions *o)
@@ -812,6 +833,7 @@ MH_API result *KernelWrapperEx(const relationshipStruct *rss, const relationship
     if (!pts || !res || !costs) { set_err("", "out of host memory", 0); goto fail; }
     clock_gettime(CLOCK_MONOTONIC, &ts[2]);
     if (KernelRun(c, iterations)) goto fail;
+    prefault(pts, sizeof(point) * (size_t)chains * (size_t)n); /* overlaps with the kernel, which is asynchronous */
     if (timing) KernelSynchronize(c);
     clock_gettime(CLOCK_MONOTONIC, &ts[3]);
     if (KernelResults(c, pts, costs)) goto fail;
