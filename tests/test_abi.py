@@ -96,3 +96,12 @@ def test_no_gpu_means_loud_failure_not_a_cpu_fallback():
     assert "failed" in str(e.value)
     with pytest.raises(pkg.KernelError):
         k.eval_costs(room, room.cfg)
+
+
+def test_missing_library_is_a_loud_error(tmp_path):
+    """No silent fallback: without libKernel.so the binding raises, it does not compute elsewhere."""
+    code = ("import importlib, sys; sys.path.insert(0, %r); p = importlib.import_module('metropolis-hastings-gpgpu_b200');\n"
+            "try:\n    p.Kernel()\nexcept p.KernelError as e:\n    print('LOUD', e)\n" % ROOT)
+    env = dict(os.environ, MH_LIB=str(tmp_path / "nope.so"))
+    out = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert "LOUD" in out.stdout and "missing" in out.stdout, out.stdout + out.stderr

@@ -238,6 +238,18 @@ def test_final_cost_distribution_matches_oracle_ks(kernel, oracle):
         assert same > 0.8, same
 
 
+def test_final_cost_distribution_config3_ks(kernel, oracle):
+    """BASELINE config 3 (the headline room, 50 objects, all terms): two-sample KS on the final
+    totalCosts of 4096 chains after 250 iterations, kernel vs oracle with disjoint seeds, and on each
+    of the weighted terms (SURVEY.md section 8d "statistical parity")."""
+    room = S.make_config(3)
+    _, ck = kernel.wrapper_ex(room, 4096, 250, seed=777)
+    _, co = oracle.run(room, 4096, 250, seed=1555)
+    for f in ("totalCosts", "SymmetryCosts", "ClearanceCosts", "PairWiseCosts", "FocalPointCosts", "SurfaceAreaCosts"):
+        p = stats.ks_2samp(ck[f], co[f]).pvalue
+        assert p > 0.005, (f, p)
+
+
 def test_frozen_objects_and_passthrough(kernel):
     room = S.make_config(1)
     room.cfg["frozen"][[1, 6]] = 1
