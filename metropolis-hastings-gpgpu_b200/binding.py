@@ -85,6 +85,11 @@ class Kernel:
 
     @staticmethod
     def _room_args(room):
+        for a, dt in ((room.rss, L.relationshipStruct), (room.rsa, L.relationshipAngleStruct), (room.cfg, L.positionAndRotation),
+                      (room.clearances, L.rectangle), (room.offlimits, L.rectangle), (room.vertices, L.vertex),
+                      (room.surfaceRectangle, L.vertex), (room.srf, L.Surface)):
+            if a.dtype != dt:                                  # e.g. np.concatenate silently repacks padded structs
+                raise KernelError(f"array has dtype of itemsize {a.dtype.itemsize}, the wire struct has {dt.itemsize}")
         return [_ptr(room.rss), _ptr(room.rsa), _ptr(room.cfg), _ptr(room.clearances), _ptr(room.offlimits), _ptr(room.vertices),
                 _ptr(room.surfaceRectangle), _ptr(room.srf)]
 
@@ -139,6 +144,8 @@ class Kernel:
     def eval_costs(self, room, layouts):
         n = room.n
         nl = len(layouts) // n
+        if layouts.dtype != L.positionAndRotation:
+            raise KernelError("layouts must have the positionAndRotation wire dtype (72-byte items)")
         out = np.zeros(nl, L.resultCosts)
         rc = self.lib.KernelEvalCosts(_ptr(room.rss), _ptr(room.rsa), _ptr(layouts), C.c_int(nl), _ptr(room.clearances),
                                       _ptr(room.offlimits), _ptr(room.vertices), _ptr(room.surfaceRectangle), _ptr(room.srf), _ptr(out))

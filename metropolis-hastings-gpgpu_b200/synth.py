@@ -196,3 +196,61 @@ def random_layouts(room, count, seed, spread=1.25, f32=True):
         for f in ("x", "y", "rotY"):
             lay[f] = lay[f].astype(np.float32).astype(np.float64)
     return lay
+
+
+def make_wild_room(n, C, R, seed):
+    """A room that breaks every convenience of make_room: the surface is an arbitrary quadrilateral
+    away from the origin, rectangles are arbitrary 4-vertex sets in arbitrary order (so the first
+    vertex is not special except through quirk Q6), several clearances may share a source, a
+    relationship may name the same object twice or use different pairs for distance and angle, the
+    focal axis has any rotation (exercising both one-sided wraps of quirk Q18), weights have any sign
+    (some zero), some objects are frozen.  Used by the parity tests only."""
+    g = np.random.default_rng(seed)
+    srf = np.zeros(1, L.Surface)
+    srf["nObjs"], srf["nRelationships"], srf["nClearances"] = n, R, C
+    for f in ("WeightFocalPoint", "WeightPairWise", "WeightVisualBalance", "WeightSymmetry", "WeightOffLimits", "WeightClearance",
+              "WeightSurfaceArea"):
+        srf[f] = 0.0 if g.random() < 0.15 else g.uniform(-3, 3)
+    ox, oy = g.uniform(-20, 20, 2)
+    W, H = g.uniform(3, 15, 2)
+    srf["centroidX"], srf["centroidY"] = ox + g.uniform(0, W), oy + g.uniform(0, H)
+    srf["focalX"], srf["focalY"] = ox + g.uniform(-1, W + 1), oy + g.uniform(-1, H + 1)
+    srf["focalRot"] = g.uniform(-2 * math.pi, 2 * math.pi)
+    sr = np.zeros(4, L.vertex)
+    corners = np.array([[ox + W, oy + H], [ox + W, oy], [ox, oy], [ox, oy + H]]) + g.uniform(-0.3, 0.3, (4, 2))
+    corners = corners[g.permutation(4)]
+    sr["x"], sr["y"] = corners[:, 0], corners[:, 1]
+    cfg = np.zeros(n, L.positionAndRotation)
+    cfg["length"] = g.uniform(0.2, 2.5, n)
+    cfg["width"] = g.uniform(0.2, 2.5, n)
+    cfg["x"] = ox + g.uniform(-1, W + 1, n)
+    cfg["y"] = oy + g.uniform(-1, H + 1, n)
+    cfg["rotY"] = g.uniform(0, 2 * L.PI, n)
+    cfg["z"] = g.uniform(-1, 1, n)
+    cfg["rotX"] = g.uniform(-1, 1, n)
+    cfg["rotZ"] = g.uniform(-1, 1, n)
+    cfg["frozen"] = (g.random(n) < 0.2).astype(np.uint8)
+    if n > 1:
+        cfg["frozen"][g.integers(n)] = 0
+    vertices = np.zeros(4 * C + 4 * n, L.vertex)
+    vertices["x"] = g.uniform(-1.5, 1.5, len(vertices))
+    vertices["y"] = g.uniform(-1.5, 1.5, len(vertices))
+    vertices["z"] = g.uniform(-1, 1, len(vertices))
+    # rectangles may start anywhere in the pool as long as 4 consecutive vertices exist
+    offl = np.zeros(n, L.rectangle)
+    for i in range(n):
+        b = int(g.integers(0, len(vertices) - 3))
+        offl[i] = (b, int(g.integers(0, 99)), int(g.integers(0, 99)), int(g.integers(0, 99)), int(g.integers(0, 99)))
+    clr = np.zeros(C, L.rectangle)
+    for c in range(C):
+        b = int(g.integers(0, len(vertices) - 3))
+        clr[c] = (b, 0, 0, 0, int(g.integers(0, n)))
+    rss = np.zeros(R, L.relationshipStruct)
+    rsa = np.zeros(R, L.relationshipAngleStruct)
+    for r in range(R):
+        s, t = int(g.integers(0, n)), int(g.integers(0, n))
+        s2, t2 = (s, t) if g.random() < 0.7 else (int(g.integers(0, n)), int(g.integers(0, n)))
+        start = g.uniform(0.2, 3.0)
+        rss[r] = (start, start + g.uniform(0.0, 3.0), s, t, g.uniform(0, 5))
+        rsa[r] = (g.uniform(0, 2 * L.PI), g.uniform(0, 2 * L.PI), s2, t2)
+    return Room(srf, rss, rsa, cfg, clr, offl, vertices, sr, f"wild room seed {seed}")

@@ -49,6 +49,7 @@ class Oracle:
 
     def costs(self, room, cfg=None, raw=False):
         cfg = room.cfg if cfg is None else cfg
+        assert cfg.dtype == mh.positionAndRotation, "layout array lost the 72-byte wire dtype"
         out = np.zeros(1, mh.resultCosts)
         raw8 = np.zeros(8, np.float64)
         self.lib.oracle_costs(_ptr(room.srf), _ptr(cfg), _ptr(room.rss), _ptr(room.rsa), _ptr(room.vertices), _ptr(room.clearances),
@@ -58,6 +59,7 @@ class Oracle:
     def costs_batch(self, room, layouts):
         n = room.n
         nl = len(layouts) // n
+        assert layouts.dtype == mh.positionAndRotation, "layout array lost the 72-byte wire dtype"
         out = np.zeros(nl, mh.resultCosts)
         self.lib.oracle_costs_batch(_ptr(room.srf), _ptr(layouts), C.c_int(nl), _ptr(room.rss), _ptr(room.rsa), _ptr(room.vertices),
                                     _ptr(room.clearances), _ptr(room.offlimits), _ptr(room.surfaceRectangle), _ptr(out))

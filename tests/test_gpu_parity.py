@@ -529,3 +529,55 @@ def test_reference_entry_point_uses_a_fresh_seed_per_call(kernel, monkeypatch):
     c, _ = kernel.wrapper(room, 32, 100)
     d, _ = kernel.wrapper(room, 32, 100)
     assert c.tobytes() == d.tobytes()
+
+
+def test_costs_and_chains_on_wild_rooms(kernel, oracle):
+    """Rooms that break every convenience of the BASELINE generator (synth.make_wild_room): cost
+    parity on the given and on random layouts, and chains that stay consistent (reported costs are the
+    cost function of the returned layouts, frozen objects stay put, memo == full scan)."""
+    for seed in range(24):
+        g = np.random.default_rng(1000 + seed)
+        n = int(g.integers(1, 40))
+        room = S.make_wild_room(n, int(g.integers(0, n + 1)), int(g.integers(0, 30)), seed)
+        lay = np.empty(16 * n, L.positionAndRotation)             # (np.concatenate would repack the struct)
+        lay[:n] = room.cfg
+        lay[n:] = S.random_layouts(room, 15, seed, spread=1.4)
+        got = kernel.eval_costs(room, lay)
+        ref = oracle.costs_batch(room, lay)
+        assert_costs_close(room, got, ref, skip_pair=near_jump(oracle, room, lay), rtol=2e-5)
+        pts, costs = kernel.wrapper_ex(room, 24, 120, seed=seed, lanes_per_chain=4, eval_mode=3)
+        pm, cm = kernel.wrapper_ex(room, 24, 120, seed=seed, lanes_per_chain=4, eval_mode=2)
+        assert pts.tobytes() == pm.tobytes() and costs.tobytes() == cm.tobytes(), seed
+        lay = layouts_from_points(room, pts)
+        assert_costs_close(room, costs, oracle.costs_batch(room, lay), skip_pair=near_jump(oracle, room, lay), rtol=2e-5)
+        fr = np.nonzero(room.cfg["frozen"])[0]
+        assert np.all(pts["x"][:, fr] == room.cfg["x"][fr].astype(np.float32))
+        # trajectories against the oracle: the bulk of the accept decisions must agree
+        with kernel.create(room, 4, seed=seed) as ctx:
+            tr = ctx.run_traced(150)
+        _, _, otr = oracle.run(room, 4, 150, seed=seed, trace=True)
+        first = [_first_divergence(tr[:, c], otr[:, c]) for c in range(4)]
+        assert sum(f is None or f > 20 for f in first) >= 3, (seed, first)
+
+
+def test_plain_c_caller_gets_the_same_bits(kernel, tmp_path, monkeypatch):
+    """tests/c/call_kernel_wrapper.c: the reference's smoke-driver room filled in by hand in C and
+    passed to KernelWrapper through include/mh_kernel.h; its output must equal the Python binding's."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    libdir = os.path.join(root, "metropolis-hastings-gpgpu_b200")
+    exe = tmp_path / "call_kernel_wrapper"
+    subprocess.run(["gcc", "-std=c11", "-O1", "-I", os.path.join(root, "include"), os.path.join(HERE, "c", "call_kernel_wrapper.c"),
+                    "-o", str(exe), "-L", libdir, "-lKernel", "-Wl,-rpath," + libdir], check=True)
+    env = dict(os.environ, MH_SEED="77")
+    out = subprocess.run([str(exe), "3", "100"], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stderr
+    monkeypatch.setenv("MH_SEED", "77")
+    pts, costs = kernel.wrapper(S.reference_main_fixture(), 3, 100)
+    lines = out.stdout.split("\n")
+    got_costs = np.array([[float.fromhex(v) for v in l.split()[2:]] for l in lines if l.startswith("costs")], np.float32)
+    got_pts = np.array([[float.fromhex(v) for v in l.split()[3:]] for l in lines if l.startswith("point")], np.float32)
+    assert got_costs.tobytes() == np.stack([costs[f] for f in L.COST_FIELDS], 1).astype(np.float32).tobytes()
+    want = np.stack([pts[f].reshape(-1) for f in ("x", "y", "z", "rotX", "rotY", "rotZ")], 1)
+    assert got_pts.tobytes() == want.astype(np.float32).tobytes()
+    assert costs["totalCosts"].min() > 3921.0        # the sampler climbs from the fixture's 3921.14

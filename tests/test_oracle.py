@@ -175,3 +175,19 @@ def test_translate_stays_inside_room(oracle):
     pts, _ = oracle.run(room, 16, 500, seed=2)
     assert pts["x"].min() >= 0 and pts["x"].max() <= 5.0 and pts["y"].min() >= 0 and pts["y"].max() <= 4.0
     assert pts["rotY"].min() >= 0 and pts["rotY"].max() <= np.float32(2 * L.PI)
+
+
+@pytest.mark.skipif(not os.path.exists(ref_host_path()), reason="oracle/_ref not built (needs /root/reference)")
+def test_bit_exact_against_reference_on_wild_rooms(oracle):
+    """Arbitrary quadrilaterals, rooms away from the origin, any focal rotation, shared clearance
+    sources, self-relationships, mixed-sign weights: the restatement must still equal the
+    reference's own code bit for bit."""
+    ref = RefHost()
+    for seed in range(40):
+        g = np.random.default_rng(seed)
+        n = int(g.integers(1, 24))
+        room = S.make_wild_room(n, int(g.integers(0, n + 1)), int(g.integers(0, 20)), seed)
+        a, ra = oracle.costs(room, raw=True)
+        b, rb = ref.costs(room, raw=True)
+        assert a.tobytes() == b.tobytes(), seed
+        assert ra.tobytes() == rb.tobytes(), seed
