@@ -314,8 +314,27 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
         surf += outside_room(a1, h);
         surf += outside_room(a2, h);
         {
-            float acc1 = 0.f, acc2 = 0.f;
-            int k = 0;
+            // The symmetry scan is bound by the MUFU pipe and the clearance overlaps by the ALU pipe
+            // (FMNMX), so the two loops are FUSED: each trip takes two symmetry columns and one
+            // clearance rectangle for both rows, and the scheduler interleaves the two instruction
+            // mixes inside one warp instead of relying on other warps being in the other phase.
+            const RowRef r1 = sym_row(h, p1), r2 = sym_row(h, p2);
+            float k1 = 5.0f, k2 = 5.0f, acc1 = 0.f, acc2 = 0.f;
+            int j = 0, k = 0;
+#ifndef MH_NO_LOOP_FUSION
+            if (!SKIP_SYM) {
+#pragma unroll 2
+                for (; j + 2 <= n && k < C; j += 2, k++) {
+                    const float4 q0 = Pc[j * CPW], q1 = Pc[(j + 1) * CPW], b0 = CBc[k * CPW];
+                    k1 = fminf(k1, sym_key(r1, q0, pi_f));
+                    k2 = fminf(k2, sym_key(r2, q0, pi_f));
+                    acc1 += overlap(a1, b0);
+                    k1 = fminf(k1, sym_key(r1, q1, pi_f));
+                    k2 = fminf(k2, sym_key(r2, q1, pi_f));
+                    acc2 += overlap(a2, b0);
+                }
+            }
+#endif
 #pragma unroll 2
             for (; k + 2 <= C; k += 2) {
                 const float4 b0 = CBc[(k + 0) * CPW], b1 = CBc[(k + 1) * CPW];
@@ -331,18 +350,16 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
             }
             clr += acc1;                                        // row order i, i+G as in the one-row form
             clr += acc2;
-        }
-        if (!SKIP_SYM) {
-            const RowRef r1 = sym_row(h, p1), r2 = sym_row(h, p2);
-            float k1 = 5.0f, k2 = 5.0f;
+            if (!SKIP_SYM) {
 #pragma unroll 4
-            for (int j = 0; j < n; j++) {
-                const float4 q = Pc[j * CPW];
-                k1 = fminf(k1, sym_key(r1, q, pi_f));
-                k2 = fminf(k2, sym_key(r2, q, pi_f));
+                for (; j < n; j++) {
+                    const float4 q = Pc[j * CPW];
+                    k1 = fminf(k1, sym_key(r1, q, pi_f));
+                    k2 = fminf(k2, sym_key(r2, q, pi_f));
+                }
+                sym += 5.0f - k1;
+                sym += 5.0f - k2;
             }
-            sym += 5.0f - k1;
-            sym += 5.0f - k2;
         }
         if (WITH_OFFLIMITS) {                                   // Kernel.cu:488-511, pairs i < j
             float acc = 0.f;

@@ -202,7 +202,7 @@ __device__ __forceinline__ float delta_rebuild(const SmemProblem &P, const WarpS
     using WS = WarpState<G>;
     constexpr int CPW = WS::CPW;
     const mhProblemHeader *h = P.h;
-    const int n = h->n, R = h->R;
+    const int R = h->R;
     RawTerms t;
     eval_terms<G, false, kDeltaStr>(P, S, c, g, t); // also refreshes S.CB
     cur.pw = t.pw; cur.pa = t.pa; cur.vbx = t.vbx; cur.vby = t.vby; cur.focal = t.focal; cur.clr = t.clr; cur.surf = t.surf;
@@ -229,7 +229,6 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
     constexpr int CPW = WS::CPW;
     const mhProblemHeader *h = P.h;
     const int n = h->n, C = h->C, R = h->R;
-    const float pi_f = 0.5f * h->two_pi;
     const float4 *Pc = S.P4 + c, *CBc = S.CB + c;
     const bool mva = a >= 0, mvb = b >= 0;
     auto inM = [&](int i) { return i == a || (mvb && i == b); };
