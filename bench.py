@@ -34,6 +34,25 @@ METRIC = "MH proposals evaluated/sec (chains x iters/s) at 50 objects"
 UNIT = "proposals/s"
 
 
+def profiled_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the chain kernel at 65536 chains,
+    from the committed `ncu --set full` summary (profiles/).  The chain state lives in shared memory, so
+    the traffic is the result block written at the end of a launch and does not depend on the iteration
+    count: it is reported to show that HBM is not the bound, not as the roofline denominator."""
+    path = os.path.join(ROOT, "profiles", "r1i_chain_n50_g4_fused_ncu_full.txt")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    try:
+        for line in open(path):
+            for key in ("dram__bytes_read.sum [", "dram__bytes_write.sum ["):
+                if line.startswith(key):
+                    unit = line[len(key):line.index("]")]
+                    total += float(line.split("=")[1]) * scale[unit]
+        return total or None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -367,7 +386,8 @@ def main():
         per_gpu_rate = float(args.chains) * args.iterations * args.steps / kernel_max
         achieved = per_gpu_rate * f_live / 1e12
         roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                    "traffic": None,
+                    "traffic": profiled_dram_traffic(),
+                    "traffic_note": "bytes per launch at 65536 chains from profiles/r1i_chain_n50_g4_fused_ncu_full.txt (result block; independent of the iteration count)",
                     "flops_per_proposal": {"live": f_live, "contract": f_contract},
                     "achieved_contract": per_gpu_rate * f_contract / 1e12, "frac_contract": per_gpu_rate * f_contract / 1e12 / peak_tflops,
                     "kernel": "mh_chain_kernel", "kernel_ms_per_launch": kernel_max * 1e3 / args.steps,

@@ -105,3 +105,17 @@ def test_missing_library_is_a_loud_error(tmp_path):
     env = dict(os.environ, MH_LIB=str(tmp_path / "nope.so"))
     out = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, env=env)
     assert "LOUD" in out.stdout and "missing" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.skipif(_has_gpu(), reason="exercises the no-GPU path of the reference arm")
+@pytest.mark.timeout(240)
+def test_bench_reference_arm_never_crashes_without_a_gpu():
+    """`bench.py --impl reference` must always print one JSON line: with no device the reference's
+    CUDA kernel cannot run, and the arm falls back to the transcribed C loop on the host cores."""
+    import json
+    out = subprocess.run([os.sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=230)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["cpu_baseline"]["cores"] >= 1 and line["e2e"]["h2d_bytes_per_step"] == 0
