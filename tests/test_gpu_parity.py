@@ -581,3 +581,21 @@ def test_plain_c_caller_gets_the_same_bits(kernel, tmp_path, monkeypatch):
     want = np.stack([pts[f].reshape(-1) for f in ("x", "y", "z", "rotX", "rotY", "rotZ")], 1)
     assert got_pts.tobytes() == want.astype(np.float32).tobytes()
     assert costs["totalCosts"].min() > 3921.0        # the sampler climbs from the fixture's 3921.14
+
+
+def test_full_size_properties_config4(kernel, oracle):
+    """BASELINE config 4 at its full chain count (262144 chains x 200 objects = 1.26 GB of results),
+    few iterations: size-independent properties -- every chain inside the room, reported costs are the
+    cost function of the returned layouts (sampled), the device arg-max agrees with the host."""
+    room = S.make_config(4)
+    with kernel.create(room, 262144, seed=5) as ctx:
+        ctx.run(12)
+        pts, costs = ctx.results()
+        bi, bt = ctx.best()
+    assert pts.shape == (262144, 200)
+    assert pts["x"].min() >= 0 and pts["x"].max() <= 20.0 and pts["y"].min() >= 0 and pts["y"].max() <= 15.0
+    assert bi == int(np.argmax(costs["totalCosts"])) and bt == costs["totalCosts"][bi]
+    sub = np.arange(0, 262144, 8192)
+    lay = layouts_from_points(room, pts[sub])
+    assert_costs_close(room, costs[sub], oracle.costs_batch(room, lay), skip_pair=near_jump(oracle, room, lay))
+    assert len(np.unique(costs["totalCosts"])) > 1000
