@@ -111,8 +111,10 @@ class ClockSampler:
 def cpu_baseline(room, target_seconds=12.0):
     """The oracle's C transcription of the per-chain loop (oracle/mh_oracle.c), one chain per
     OpenMP thread on all host cores, on a bounded sample of the same workload."""
-    from oracle_lib import Oracle
-    o = Oracle()
+    from oracle_lib import Oracle, build_native_oracle
+    native = build_native_oracle()
+    o = Oracle(native) if native else Oracle()
+    flags = "gcc -O2 -march=native" if native else "gcc -O2"
     try:                                       # torchrun pins OMP_NUM_THREADS=1: ask for the real core count
         threads = len(os.sched_getaffinity(0))
     except AttributeError:
@@ -123,7 +125,7 @@ def cpu_baseline(room, target_seconds=12.0):
     iters = max(20, int(rate * target_seconds / chains))
     _, _, secs, th = o.run(room, chains, iters, seed=1, timed=True, threads=threads)
     return {"value": chains * iters / secs, "unit": UNIT, "cores": th, "kind": "port",
-            "sample": f"{chains} chains x {iters} iterations of the same room ({secs:.1f} s), gcc -O2, OpenMP"}
+            "sample": f"{chains} chains x {iters} iterations of the same room ({secs:.1f} s), {flags} -ffp-contract=off, OpenMP"}
 
 
 def reference_gpu(config_id, chains, iters, steps, warmup, timeout_s=300):

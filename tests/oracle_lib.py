@@ -28,9 +28,24 @@ def build_oracle():
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s"], check=True)
 
 
+def build_native_oracle():
+    """The same mh_oracle.c compiled for THIS host's CPU (-march=native), for the timed CPU baseline
+    (BASELINE.md section 2(b)); the portable build stays the checker.  Returns a path or None."""
+    import subprocess
+    import tempfile
+    out = os.path.join(tempfile.gettempdir(), f"liboracle_native_{os.getuid()}.so")
+    src = os.path.join(ROOT, "oracle", "mh_oracle.c")
+    try:
+        subprocess.run(["gcc", "-std=c11", "-O2", "-march=native", "-ffp-contract=off", "-fopenmp", "-fvisibility=hidden", "-shared",
+                        "-fPIC", "-o", out, src, "-lm"], check=True, capture_output=True, timeout=120)
+        return out
+    except Exception:
+        return None
+
+
 class Oracle:
-    def __init__(self):
-        path = os.path.join(ROOT, "oracle", "liboracle.so")
+    def __init__(self, path=None):
+        path = path or os.path.join(ROOT, "oracle", "liboracle.so")
         if not os.path.exists(path):
             build_oracle()
         self.lib = C.CDLL(path)
