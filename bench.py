@@ -120,8 +120,9 @@ def cpu_baseline(room, target_seconds=12.0):
     except AttributeError:
         threads = os.cpu_count() or 1
     chains = threads * 4
-    _, _, secs, th = o.run(room, chains, 20, seed=1, timed=True, threads=threads)          # calibrate
-    rate = chains * 20 / max(secs, 1e-6)
+    o.run(room, chains, 20, seed=1, timed=True, threads=threads)                           # wake the thread pool
+    _, _, secs, th = o.run(room, chains, 400, seed=1, timed=True, threads=threads)         # calibrate
+    rate = chains * 400 / max(secs, 1e-6)
     iters = max(20, int(rate * target_seconds / chains))
     _, _, secs, th = o.run(room, chains, iters, seed=1, timed=True, threads=threads)
     return {"value": chains * iters / secs, "unit": UNIT, "cores": th, "kind": "port",
