@@ -32,6 +32,10 @@
 namespace mh {
 
 constexpr int kSymUnroll = MH_SYM_UNROLL; // columns per trip of the symmetry loop
+#ifndef MH_FUSE_UNROLL
+#define MH_FUSE_UNROLL 2
+#endif
+constexpr int kFuseUnroll = MH_FUSE_UNROLL; // trips of the fused symmetry+clearance loop unrolled together
 
 struct SmemProblem {
     const mhProblemHeader *h;
@@ -323,7 +327,7 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
             int j = 0, k = 0;
 #ifndef MH_NO_LOOP_FUSION
             if (!SKIP_SYM) {
-#pragma unroll 2
+#pragma unroll kFuseUnroll
                 for (; j + 2 <= n && k < C; j += 2, k++) {
                     const float4 q0 = Pc[j * CPW], q1 = Pc[(j + 1) * CPW], b0 = CBc[k * CPW];
                     k1 = fminf(k1, sym_key(r1, q0, pi_f));

@@ -2,9 +2,8 @@
 # development probe: A/B of experimental libKernel builds (MH_LIB); "base" = the product build
 for v in "$@"; do
   lib=$PWD/metropolis-hastings-gpgpu_b200/libKernel_$v.so; [ "$v" = base ] && lib=$PWD/metropolis-hastings-gpgpu_b200/libKernel.so
-  for l in 4 8; do echo -n "$v "; MH_LIB=$lib python tests/prof_target.py 3 65536 400 $l 3 | tail -1; done
-  echo -n "$v "; MH_LIB=$lib python tests/prof_target.py 4 16384 60 32 3 | tail -1
+  echo -n "$v "; MH_LIB=$lib python tests/prof_target.py 3 65536 400 4 3 | tail -1
+  echo -n "$v "; MH_LIB=$lib python tests/prof_target.py 3 65536 400 4 3 | tail -1
   echo -n "$v "; MH_LIB=$lib python tests/prof_target.py 2 65536 1000 2 3 | tail -1
-  echo -n "$v "; MH_LIB=$lib python tests/prof_target.py 1 65536 2000 1 3 | tail -1
   echo -n "$v "; MH_LIB=$lib python tests/prof_target.py 40,40,40 65536 400 0 3 | tail -1
 done
