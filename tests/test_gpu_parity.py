@@ -200,6 +200,31 @@ def test_fixed_seed_trajectory_matches_oracle(kernel, oracle):
     assert full >= 26, full
 
 
+@pytest.mark.parametrize("cid,iters", [(2, 600), (3, 400)])
+def test_trajectories_match_oracle_on_larger_rooms(kernel, oracle, cid, iters):
+    """The accept/reject sequences of 24 chains on the 16- and 50-object rooms: most chains must
+    follow the oracle's serial chain move for move, and wherever one parts the oracle's u must sit on
+    the acceptance threshold (float32 vs the reference's mixed precision can decide only ties)."""
+    room = S.make_config(cid)
+    with kernel.create(room, 24, seed=31) as ctx:
+        tr = ctx.run_traced(iters)
+    _, _, otr = oracle.run(room, 24, iters, seed=31, trace=True)
+    c0 = oracle.costs(room)["totalCosts"]
+    full = 0
+    for c in range(24):
+        k = _first_divergence(tr[:, c], otr[:, c])
+        if k is None:
+            full += 1
+            np.testing.assert_allclose(tr["star_total"][:, c], otr["star_total"][:, c], rtol=3e-5, atol=3e-3)
+            continue
+        o = otr[:, c]
+        assert tr["move"][k, c] == o["move"][k] and tr["obj1"][k, c] == o["obj1"][k] and tr["obj2"][k, c] == o["obj2"][k]
+        prev = o["cur_total"][k - 1] if k else c0
+        thr = min(1.0, float(np.exp(2.0 * (float(o["star_total"][k]) - float(prev)))))
+        assert abs(float(o["u"][k]) - thr) < 5e-3 * max(thr, 1e-3), (c, k, o["u"][k], thr)
+    assert full >= 18, full
+
+
 def test_sharded_run_equals_unsharded(kernel):
     """Chains are keyed by GLOBAL chain id: splitting a run over calls /
     GPUs must not change any chain."""
