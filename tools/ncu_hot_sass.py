@@ -1,5 +1,5 @@
 """Lists the hottest SASS regions of an .ncu-rep by executed instructions:
-python tests/ncu_hot_sass.py rep [min_fraction]"""
+python tools/ncu_hot_sass.py rep [min_fraction]"""
 import csv, subprocess, sys
 rep = sys.argv[1]
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True, check=True).stdout

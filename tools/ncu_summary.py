@@ -1,5 +1,5 @@
 """Condenses an .ncu-rep (read here, no GPU needed) into the handful of numbers DESIGN.md and
-the judge need: python tests/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x.txt"""
+the judge need: python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x.txt"""
 import csv
 import subprocess
 import sys

@@ -1,6 +1,6 @@
 """Throughput of the chain kernel per lane width (development probe, not a test)."""
 import importlib, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (tools/ sits one level below)
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("metropolis-hastings-gpgpu_b200")
 k = pkg.Kernel()

@@ -1,7 +1,7 @@
 """Profiling target: one warm-up launch and one measured launch of the chain kernel.
 usage: prof_target.py <config id> <chains> <iterations> [lanes]"""
 import importlib, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (tools/ sits one level below)
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("metropolis-hastings-gpgpu_b200")
 spec = sys.argv[1]
