@@ -302,11 +302,13 @@ def test_best_mode_and_annealing(kernel, oracle):
     ref = oracle.costs_batch(room, layouts_from_points(room, pb))
     assert_costs_close(room, cb, ref, skip_pair=near_jump(oracle, room, layouts_from_points(room, pb)))
     # annealing: a rising beta ends higher (the sampler maximises totalCosts, quirk Q10)
-    _, ca = kernel.wrapper_ex(room, 1024, 600, seed=9, beta_start=0.5, beta_end=16.0, schedule=1)
-    _, c2 = kernel.wrapper_ex(room, 1024, 600, seed=9)
+    _, ca = kernel.wrapper_ex(room, 4096, 600, seed=3, beta_start=0.5, beta_end=16.0, schedule=1)
+    _, c2 = kernel.wrapper_ex(room, 4096, 600, seed=3)
     assert ca["totalCosts"].mean() > c2["totalCosts"].mean()
-    _, oa = oracle.run(room, 1024, 600, seed=10, beta_start=0.5, beta_end=16.0, schedule=1)
-    assert stats.ks_2samp(ca["totalCosts"], oa["totalCosts"]).pvalue > 0.01
+    _, oa = oracle.run(room, 4096, 600, seed=4, beta_start=0.5, beta_end=16.0, schedule=1)
+    assert stats.ks_2samp(ca["totalCosts"], oa["totalCosts"]).pvalue > 0.01      # 0.87 when written (tools/ks_margins.py)
+    _, os_ = oracle.run(room, 512, 600, seed=3, beta_start=0.5, beta_end=16.0, schedule=1)
+    assert np.isclose(ca["totalCosts"][:512], os_["totalCosts"], rtol=1e-4, atol=1e-3).mean() > 0.9
 
 
 def test_kernel_best_is_argmax(kernel):
@@ -433,8 +435,8 @@ def test_delta_with_frozen_best_and_annealing(kernel, oracle):
     _, cf = kernel.wrapper_ex(room, 256, 300, seed=9, eval_mode=1)
     pb, cb = kernel.wrapper_ex(room, 256, 300, seed=9, eval_mode=1, result_mode=1)
     assert np.all(cb["totalCosts"] >= cf["totalCosts"] - 1e-2)
-    _, ca = kernel.wrapper_ex(room, 1024, 600, seed=9, eval_mode=1, beta_start=0.5, beta_end=16.0, schedule=1)
-    _, oa = oracle.run(room, 1024, 600, seed=10, beta_start=0.5, beta_end=16.0, schedule=1)
+    _, ca = kernel.wrapper_ex(room, 4096, 600, seed=3, eval_mode=1, beta_start=0.5, beta_end=16.0, schedule=1)
+    _, oa = oracle.run(room, 4096, 600, seed=4, beta_start=0.5, beta_end=16.0, schedule=1)
     assert stats.ks_2samp(ca["totalCosts"], oa["totalCosts"]).pvalue > 0.01
 
 
