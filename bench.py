@@ -267,6 +267,10 @@ def run_reference_arm(args, room, rank):
                     cpu_baseline={"value": v_wall, "unit": UNIT, "cores": 0, "kind": "reference",
                                   "sample": f"{chains} chains x {iters} iterations; the reference's path is a CUDA kernel, timed on the same B200 (device-event rate {v_dev:.4g}/s)"},
                     e2e={"value": v_wall, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
+        try:   # the other baseline of BASELINE.md section 2, beside it: the transcribed C loop on the host cores
+            line["cpu_port_baseline"] = cpu_baseline(room, target_seconds=5.0)
+        except Exception as ex2:
+            line["cpu_port_baseline"] = {"unavailable": str(ex2)}
     except Exception as ex:  # no GPU build of the reference: its algorithm as transcribed C on the host cores
         cb = cpu_baseline(room, target_seconds=max(5.0, 4.0 * args.steps))
         cb["sample"] += f" (reference kernel unavailable: {ex})"
