@@ -164,6 +164,11 @@ MH_API int KernelSetStream(mhContext *ctx, void *stream);
 /* Index (local to this context) and totalCosts of the chain with the highest totalCosts
  * (the sampler maximises totalCosts, quirk Q10); reduced on the device. */
 MH_API int KernelBest(mhContext *ctx, int *bestChain, float *bestTotal);
+/* The k chains with the highest totalCosts, best first (ties: lower chain index first): indices local
+ * to this context and their totals (either output may be NULL).  Returns how many were written
+ * (min(k, nChains)) or -1.  The ranking the reference leaves to its caller (it cannot rank: its costs
+ * are garbage, quirk Q3). */
+MH_API int KernelTopK(mhContext *ctx, int k, int *chains, float *totals);
 /* Multi-GPU arg-best: writes to the DEVICE address d_key one signed 64-bit key that orders like
  * (totalCosts of this context's best chain, lower global chain id first).  A MAX all-reduce of
  * the keys over all ranks (NCCL has no arg-max) yields the global best; KernelDecodeBestKey

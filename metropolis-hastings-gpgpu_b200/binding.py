@@ -17,7 +17,7 @@ _P = C.c_void_p
 
 EXPORTS = ("KernelWrapper", "KernelWrapperEx", "KernelFree", "KernelLastError", "KernelEvalCosts", "KernelCreate", "KernelRun",
            "KernelRunTraced", "KernelSynchronize", "KernelResults", "KernelDeviceResults", "KernelSetStream", "KernelBest",
-           "KernelStats", "KernelDestroy", "KernelDeviceInfo", "KernelBestKey", "KernelDecodeBestKey", "KernelReset", "KernelTrim", "KernelTemperingState", "KernelTemperingExchange")
+           "KernelStats", "KernelDestroy", "KernelDeviceInfo", "KernelBestKey", "KernelDecodeBestKey", "KernelReset", "KernelTrim", "KernelTemperingState", "KernelTemperingExchange", "KernelTopK")
 
 
 class KernelError(RuntimeError):
@@ -69,6 +69,7 @@ class Kernel:
             lib.KernelSetStream.argtypes = [_P, _P]
             lib.KernelBestKey.argtypes = [_P, _P]
             lib.KernelReset.argtypes = [_P]
+            lib.KernelTopK.argtypes = [_P, C.c_int, _P, _P]
             lib.KernelTemperingState.argtypes = [_P, C.POINTER(_P), C.POINTER(_P)]
             lib.KernelTemperingExchange.argtypes = [_P, _P, _P]
             lib.KernelDecodeBestKey.argtypes = [C.c_longlong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]
@@ -240,6 +241,14 @@ class Context:
     def reset(self):
         if self.k.lib.KernelReset(self.h) != 0:
             self.k._fail("KernelReset")
+
+    def top_k(self, k):
+        idx = np.zeros(k, np.int32)
+        tot = np.zeros(k, np.float32)
+        m = self.k.lib.KernelTopK(self.h, C.c_int(k), _ptr(idx), _ptr(tot))
+        if m < 0:
+            self.k._fail("KernelTopK")
+        return idx[:m], tot[:m]
 
     def stats(self):
         ms, n = C.c_double(), C.c_longlong()

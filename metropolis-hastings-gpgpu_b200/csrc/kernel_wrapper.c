@@ -705,6 +705,43 @@ fail:
     return rc;
 }
 
+typedef struct rankItem { float total; int32_t chain; } rankItem;
+
+static int rank_cmp(const void *a, const void *b)
+{
+    const rankItem *x = (const rankItem *)a, *y = (const rankItem *)b;
+    if (x->total != y->total) return x->total > y->total ? -1 : 1; /* NaN sorts wherever; totals are finite in practice */
+    return x->chain < y->chain ? -1 : (x->chain > y->chain);
+}
+
+MH_API int KernelTopK(mhContext *ctx, int k, int *chains, float *totals)
+{
+    int prev = -1, rc = -1;
+    resultCosts *hc = NULL;
+    rankItem *items = NULL;
+    g_err[0] = 0;
+    if (!ctx || k < 1) { set_err("", "bad arguments", 0); return -1; }
+    if (k > ctx->n_chains) k = ctx->n_chains;
+    hc = (resultCosts *)malloc(sizeof(resultCosts) * (size_t)ctx->n_chains);
+    items = (rankItem *)malloc(sizeof(rankItem) * (size_t)ctx->n_chains);
+    if (!hc || !items) { set_err("", "out of host memory", 0); goto fail; }
+    CU(enter_device(ctx->device, &prev));
+    CU(ensure_scored(ctx));
+    CU(mhdev_d2h(hc, ctx->d_costs, sizeof(resultCosts) * (size_t)ctx->n_chains, ctx->stream));
+    CU(mhdev_stream_sync(ctx->stream));
+    for (int i = 0; i < ctx->n_chains; i++) { items[i].total = hc[i].totalCosts; items[i].chain = i; }
+    qsort(items, (size_t)ctx->n_chains, sizeof(rankItem), rank_cmp);
+    for (int i = 0; i < k; i++) {
+        if (chains) chains[i] = items[i].chain;
+        if (totals) totals[i] = items[i].total;
+    }
+    rc = k;
+fail:
+    free(hc); free(items);
+    if (prev >= 0) leave_device(ctx->device, prev);
+    return rc;
+}
+
 MH_API int KernelBestKey(mhContext *ctx, void *d_key)
 {
     int prev = -1, rc = -1;

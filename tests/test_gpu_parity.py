@@ -320,6 +320,13 @@ def test_kernel_best_is_argmax(kernel):
         ms, launches = ctx.stats()
     assert i == int(np.argmax(c["totalCosts"])) and t == c["totalCosts"][i]
     assert ms > 0 and launches >= 2
+    with kernel.create(room, 1000, seed=4) as ctx:
+        ctx.run(100)
+        idx, tot = ctx.top_k(10)
+        _, c = ctx.results()
+        big, _ = ctx.top_k(5000)
+    order = np.lexsort((np.arange(1000), -c["totalCosts"]))
+    assert np.array_equal(idx, order[:10]) and np.array_equal(tot, c["totalCosts"][order[:10]]) and len(big) == 1000
 
 
 def test_full_size_properties_config3(kernel, oracle):
