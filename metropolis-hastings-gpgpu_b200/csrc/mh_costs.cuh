@@ -29,6 +29,15 @@
 #define MH_SYM_UNROLL 8
 #endif
 
+// Block barriers at phase boundaries of the memo / delta kernels (see mh_kernels.cu: MH_SYNC_ITER).
+#ifndef MH_SYNC_ITER
+#define MH_SYNC_ITER 0
+#endif
+#define MH_PHASE_SYNC(level)                  \
+    do {                                      \
+        if (MH_SYNC_ITER >= (level)) __syncthreads(); \
+    } while (0)
+
 namespace mh {
 
 constexpr int kSymUnroll = MH_SYM_UNROLL; // columns per trip of the symmetry loop

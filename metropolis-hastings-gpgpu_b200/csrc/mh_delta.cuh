@@ -154,6 +154,7 @@ __device__ __forceinline__ float sym_memo_eval(const SmemProblem &P, const WarpS
             D.km(1 - sel, i, c) = make_float2(k, __int_as_float(arg));
         }
     }
+    MH_PHASE_SYNC(3);
     // ---- rows rescanned by the whole group.  The moved rows a and b share one pass over the columns;
     //      rows whose remembered column moved are taken one per trip, each group picking its own next
     //      row, so the warp pays for the longest group queue. -----------------------------------------------
@@ -264,6 +265,7 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
         }
     }
 
+    MH_PHASE_SYNC(3);
     // ---- clearances: pairs (k, moved object) for every k; Q7 surface of clearance INDEX a / b ------
     if (mva) {
         for (int k = g; k < C; k += G) {
@@ -301,6 +303,7 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
         }
     }
 
+    MH_PHASE_SYNC(3);
     // ---- relationships that name a moved object: first collect them per lane, then evaluate slot by
     //      slot, so that the warp pays for the deepest lane queue and not for every loop trip in
     //      which some lane happens to hold one ------------------------------------------------------------
@@ -342,6 +345,7 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
     MH_REL_SLOT(stash.r3, stash.v3)
 #undef MH_REL_SLOT
 
+    MH_PHASE_SYNC(3);
     // ---- symmetry: exact memo (sym_memo_eval) ---------------------------------------------------------------
     const float sym_total = sym_memo_eval<G, kDeltaStr>(P, S, D, c, g, sel, a, b, na, nb);
 

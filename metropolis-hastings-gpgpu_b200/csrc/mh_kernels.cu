@@ -24,7 +24,10 @@
 
 namespace mh {
 
-constexpr int WARPS_PER_BLOCK = 4;
+#ifndef MH_WARPS_PER_BLOCK
+#define MH_WARPS_PER_BLOCK 4
+#endif
+constexpr int WARPS_PER_BLOCK = MH_WARPS_PER_BLOCK;
 constexpr int THREADS = WARPS_PER_BLOCK * 32;
 #ifndef MH_MEMO_MIN_BLOCKS
 #define MH_MEMO_MIN_BLOCKS 5 // same for the memo / delta forms
@@ -174,6 +177,7 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
                                                     : L.beta_start + (L.beta_end - L.beta_start) * tt;
         }
 
+        if (MODE != 0) MH_PHASE_SYNC(1);
         if (DELTA && k > 0 && (it % (uint64_t)kRefresh) == 0)   // bound the drift of the running sums
             cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);
 
@@ -222,6 +226,7 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
         }
         __syncwarp();
 
+        if (MODE != 0) MH_PHASE_SYNC(2);
         // -- evaluate the proposal (Kernel.cu:804): every live term, from scratch -- or, in delta
         //    mode, only what the moved objects touch ---------------------------------------------------
         float star;
@@ -241,6 +246,7 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
             star = combine(h, t).total;
         }
 
+        if (MODE != 0) MH_PHASE_SYNC(2);
         // -- accept (Kernel.cu:706-713): u < min(1, exp(beta (star - cur))), maximises (Q10) ------
         const float u = uniform01(draw_block(L.seed, gchain, it, 1).x);
         const bool acc = accept_move(u, beta, star, cur);
