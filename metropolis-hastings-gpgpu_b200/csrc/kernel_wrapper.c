@@ -152,6 +152,8 @@ static int pack_problem(const relationshipStruct *rss, const relationshipAngleSt
     H.off_clr_src = w;    w = align4(w + C);
     H.off_clr_adj_off = w; w = align4(w + n + 1);
     H.off_clr_adj = w;    w = align4(w + C);
+    H.off_rel_adj_off = w; w = align4(w + n + 1);
+    H.off_rel_adj = w;    w = align4(w + 4 * R);
     H.smem_words = w;
     H.off_cfg0 = w;       w = align4(w + 3 * n);
     H.off_pass = w;       w = align4(w + 3 * n);
@@ -239,6 +241,25 @@ static int pack_problem(const relationshipStruct *rss, const relationshipAngleSt
         rng[0] = (float)(1.0 / start); rng[1] = (float)end; rng[2] = (float)amin; rng[3] = (float)amax;
         aux[0] = (float)start; aux[1] = (float)(1.0 / norm); aux[2] = wraps ? 1.f : 0.f; aux[3] = 0.f;
     }
+    {   /* CSR: relationships by object, each relationship at most once per object (delta evaluation) */
+        int *cnt = (int *)calloc((size_t)n + 1, sizeof(int));
+        if (!cnt) { free(b); set_err("", "out of host memory", 0); return -1; }
+        for (int pass = 0; pass < 2; pass++) {
+            for (int i = 0; i < R; i++) {
+                const int32_t *id = bi + H.off_rel_idx + 4 * i;
+                for (int q = 0; q < 4; q++) {
+                    int seen = 0;
+                    for (int p = 0; p < q; p++) seen |= id[p] == id[q];
+                    if (seen) continue;
+                    if (pass == 0) bi[H.off_rel_adj_off + id[q] + 1]++;
+                    else bi[H.off_rel_adj + bi[H.off_rel_adj_off + id[q]] + cnt[id[q]]++] = i;
+                }
+            }
+            if (pass == 0)
+                for (int i = 0; i < n; i++) bi[H.off_rel_adj_off + i + 1] += bi[H.off_rel_adj_off + i];
+        }
+        free(cnt);
+    }
     memcpy(b, &H, sizeof H);
     out->blob = b;
     out->h = (mhProblemHeader *)b;
@@ -253,7 +274,7 @@ typedef struct evPair { void *e0, *e1; } evPair;
 
 struct mhContext {
     int device;        /* device the context lives on */
-    int n, C, R, n_chains, lanes, score_lanes;
+    int n, C, R, n_chains, lanes, score_lanes, delta_warps;
     int eval_internal; /* what the chain kernel runs: 0 full scan, 1 delta, 2 exact symmetry memo */
     mhOptions opt;
     int problem_words, smem_words;
@@ -302,7 +323,7 @@ static int choose_lanes(int n, int C, int R, int smem_words, int n_chains, int r
     double best_score = -1.0;
     for (int k = 0; k < 6; k++) {
         const int G = cand[k];
-        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, eval_mode);
+        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, eval_mode, 4);
         if (bytes < 0 || bytes > max_block) continue;
         if (requested == G) return G;
         int blocks_per_sm = max_sm / (bytes + 1024);
@@ -324,6 +345,43 @@ static int choose_lanes(int n, int C, int R, int smem_words, int n_chains, int r
     }
     if (best < 0) snprintf(g_err, sizeof g_err, "problem does not fit in shared memory (n=%d, C=%d)", n, C);
     return best;
+}
+
+/* Launch shape of the delta kernel (mh_delta_kernel): lanes per chain and warps per block.
+ * Its per-proposal work is ~(fixed scalar part) + (3n + 2C)/G pair evaluations per lane, and the fixed
+ * part is repeated by every lane of a group, so narrow groups win as long as a lane keeps 6-8 rows
+ * (measured on B200: n=8 -> 1, n=16 -> 2, n=50 -> 8, n=200 -> 32 lanes).  Few chains: widen the groups
+ * until the machine is covered.  Blocks of 8 warps (two per SM, with the per-iteration barrier that keeps
+ * their instruction fetch together) when shared memory allows and the grid still covers the SMs. */
+static int choose_delta_shape(int n, int C, int R, int smem_words, int n_chains, int requested, int *lanes_out, int *warps_out)
+{
+    int max_block = 0, max_sm = 0, sms = 0;
+    int e = mhdev_device_limits(&max_block, &max_sm, &sms, NULL, NULL, NULL, NULL, 0);
+    if (e) { set_err("%s failed: %s", "device query", e); return -1; }
+    const char *env = getenv("MH_LANES");
+    if (requested <= 0 && env) requested = atoi(env);
+    int G = 1;
+    while (G < 32 && G * 8 < n) G *= 2;
+    while (G < 32 && (double)n_chains * G / 32.0 < 8.0 * sms) G *= 2;      /* under-filled machine: wider groups */
+    if (requested > 0) G = requested;
+    for (;; G *= 2) {                                                       /* must fit with 4 warps per block */
+        if (G > 32) { snprintf(g_err, sizeof g_err, "problem does not fit in shared memory (n=%d, C=%d, delta evaluation)", n, C); return -1; }
+        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, MH_EVAL_DELTA, 4);
+        if (bytes >= 0 && bytes <= max_block) break;
+        if (requested > 0) { snprintf(g_err, sizeof g_err, "lanes_per_chain=%d does not fit in shared memory (delta evaluation)", G); return -1; }
+    }
+    int warps = 8;                                                          /* measured: 8 >= 16 > 4 at n = 50 and n = 200 */
+    const char *wenv = getenv("MH_DELTA_WARPS");
+    if (wenv) warps = atoi(wenv) >= 16 ? 16 : atoi(wenv) >= 8 ? 8 : 4;
+    const double total_warps = ceil((double)n_chains * G / 32.0);
+    while (warps > 4) {
+        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, MH_EVAL_DELTA, warps);
+        if (bytes >= 0 && bytes <= max_block && (wenv || total_warps / warps >= (double)sms)) break;
+        warps /= 2;
+    }
+    *lanes_out = G;
+    *warps_out = warps;
+    return 0;
 }
 
 static void ctx_free(mhContext *c)
@@ -439,7 +497,11 @@ MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationship
         if (c->lanes > 0) c->eval_internal = MH_EVAL_MEMO;
         g_err[0] = 0;
     }
-    if (c->lanes < 0) c->lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, c->eval_internal);
+    if (c->eval_internal == MH_EVAL_DELTA) {
+        if (choose_delta_shape(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, &c->lanes, &c->delta_warps)) goto fail;
+    } else if (c->lanes < 0) {
+        c->lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, c->eval_internal);
+    }
     if (c->lanes < 0) goto fail;
     /* a pinned lane width also pins the scoring kernel, so that sharded runs report identical bits */
     c->score_lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, MH_EVAL_FULL);
@@ -518,6 +580,7 @@ static int launch_segment(mhContext *c, int iterations, void *d_trace)
     L.schedule_length = c->opt.schedule_length;
     L.result_mode = c->opt.result_mode;
     L.eval_mode = c->eval_internal;
+    L.warps_per_block = c->delta_warps;
     L.beta_start = (float)c->opt.beta_start; L.beta_end = (float)c->opt.beta_end;
     L.beta_log2_ratio = log2f((float)(c->opt.beta_end / c->opt.beta_start));
     L.d_x = c->d_x; L.d_y = c->d_y; L.d_rot = c->d_rot; L.d_perm = c->d_perm; L.d_cur_total = c->d_cur;

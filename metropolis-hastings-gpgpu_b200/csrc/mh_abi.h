@@ -47,7 +47,9 @@ typedef struct mhProblemHeader {
     int32_t off_cfg0;       /* float[3n] x, y, rotY of the caller's layout (global only)       */
     int32_t off_pass;       /* float[3n] z, rotX, rotZ pass-through, narrowed (global only)    */
     int32_t total_words;
-    int32_t pad1, pad2, pad3, pad4;
+    int32_t off_rel_adj_off; /* int32[n+1] CSR offsets: relationships that name object i (any of the 4 indices) */
+    int32_t off_rel_adj;    /* int32[<=4R] CSR list of relationship indices, each at most once per object   */
+    int32_t pad3, pad4;
 } mhProblemHeader;
 
 enum { MH_SCHED_CONSTANT = 0, MH_SCHED_GEOMETRIC = 1, MH_SCHED_LINEAR = 2, MH_SCHED_PER_CHAIN = 3 };
@@ -70,7 +72,7 @@ typedef struct mhLaunch {
     int32_t schedule_length;
     int32_t result_mode;    /* 0 final layout, 1 best layout                                   */
     int32_t eval_mode;      /* 0 full re-evaluation per proposal, 1 delta evaluation            */
-    int32_t pad_i;
+    int32_t warps_per_block; /* delta kernel only: 4, 8 or 16 (the other forms are compiled for 4) */
     float beta_start;
     float beta_end;
     float beta_log2_ratio;  /* log2f(beta_end/beta_start)                                      */
@@ -105,7 +107,8 @@ int mhdev_launch_bestkey(const void *d_argmax_out, uint64_t chain_offset, uint64
 /* Largest dynamic shared memory per block and SM count / clock of the current device. */
 int mhdev_device_limits(int *max_smem_per_block, int *max_smem_per_sm, int *sm_count, int *clock_khz, int *cc_major,
                         int *cc_minor, char *name, int name_len);
-int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int eval_mode);
+/* Dynamic shared memory of one block of the chain kernel; `warps` matters for the delta form only. */
+int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int eval_mode, int warps);
 
 /* raw runtime helpers */
 int mhdev_get_device(int *dev);

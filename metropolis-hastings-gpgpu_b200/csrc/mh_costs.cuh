@@ -29,15 +29,6 @@
 #define MH_SYM_UNROLL 8
 #endif
 
-// Block barriers at phase boundaries of the memo / delta kernels (see mh_kernels.cu: MH_SYNC_ITER).
-#ifndef MH_SYNC_ITER
-#define MH_SYNC_ITER 0
-#endif
-#define MH_PHASE_SYNC(level)                  \
-    do {                                      \
-        if (MH_SYNC_ITER >= (level)) __syncthreads(); \
-    } while (0)
-
 namespace mh {
 
 constexpr int kSymUnroll = MH_SYM_UNROLL; // columns per trip of the symmetry loop
@@ -57,6 +48,8 @@ struct SmemProblem {
     const int *clr_src;
     const int *clr_adj_off;
     const int *clr_adj;
+    const int *rel_adj_off;
+    const int *rel_adj;
     const int4 *rel_idx;
     const float4 *rel_rng;
     const float4 *rel_aux;
@@ -75,6 +68,8 @@ __device__ __forceinline__ SmemProblem bind_problem(const float *base)
     P.clr_src = reinterpret_cast<const int *>(base + P.h->off_clr_src);
     P.clr_adj_off = reinterpret_cast<const int *>(base + P.h->off_clr_adj_off);
     P.clr_adj = reinterpret_cast<const int *>(base + P.h->off_clr_adj);
+    P.rel_adj_off = reinterpret_cast<const int *>(base + P.h->off_rel_adj_off);
+    P.rel_adj = reinterpret_cast<const int *>(base + P.h->off_rel_adj);
     P.rel_idx = reinterpret_cast<const int4 *>(base + P.h->off_rel_idx);
     P.rel_rng = reinterpret_cast<const float4 *>(base + P.h->off_rel_rng);
     P.rel_aux = reinterpret_cast<const float4 *>(base + P.h->off_rel_aux);

@@ -72,11 +72,13 @@ template <int G, bool STR> __device__ __forceinline__ int group_min_int(int v)
     return v;
 }
 
-// Relationship penalties a proposal recomputed, kept in registers until the accept decision.
+// Relationship penalties a proposal recomputed, kept in registers until the accept decision.  The
+// relationships that name a moved object are dealt round-robin to the lanes of the group, so a lane
+// rarely holds more than one; beyond two the commit recomputes.
 struct RelStash {
-    int r0, r1, r2, r3;
-    float2 v0, v1, v2, v3;
-    int overflow; // more than four touched relationships in this lane: commit recomputes
+    int r0, r1;
+    float2 v0, v1;
+    int overflow; // some lane of the group held more than two: the commit recomputes the touched ones
 };
 
 // Minimum of key(row, j) over j = j0, j0+step, ... and a column attaining it.
@@ -154,7 +156,6 @@ __device__ __forceinline__ float sym_memo_eval(const SmemProblem &P, const WarpS
             D.km(1 - sel, i, c) = make_float2(k, __int_as_float(arg));
         }
     }
-    MH_PHASE_SYNC(3);
     // ---- rows rescanned by the whole group.  The moved rows a and b share one pass over the columns;
     //      rows whose remembered column moved are taken one per trip, each group picking its own next
     //      row, so the warp pays for the longest group queue. -----------------------------------------------
@@ -218,9 +219,16 @@ __device__ __forceinline__ float delta_rebuild(const SmemProblem &P, const WarpS
     return combine(h, t).total;
 }
 
-// Evaluate the proposal that moved objects a (and b; -1 = none) from oa/ob to na/nb; S.P4 already
-// holds the new state.  Writes the proposal's KM memo into buffer 1-sel, returns its total and
-// its running sums.  Every lane of the warp must call this.
+// Evaluate the proposal that moved object a (and b; -1 = none) from oa/ob to na/nb; S.P4 already
+// holds the new state.  Writes the proposal's KM memo into buffer 1-sel, returns its total and its
+// running sums.  Every lane of the warp must call this.
+//
+// The code is written for a warp that holds several chains whose moves differ: there is no branch
+// on the move type.  A one-object move is evaluated as a two-object move whose second object has an
+// empty rectangle (its overlaps are exactly zero) and repeats the first object's symmetry column;
+// loop trip counts that depend on the move (clearances sourced at a moved object, relationships that
+// name one, rows to rescan) are the maximum over the warp, lanes without work evaluate a dummy and
+// drop the result.
 template <int G>
 __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, const int c, const int g,
                                             const int sel, const int a, const int b, const float4 oa, const float4 ob, const float4 na,
@@ -228,126 +236,194 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
 {
     using WS = WarpState<G>;
     constexpr int CPW = WS::CPW;
+    constexpr unsigned FULL = 0xffffffffu;
     const mhProblemHeader *h = P.h;
-    const int n = h->n, C = h->C, R = h->R;
+    const int n = h->n, C = h->C;
     const float4 *Pc = S.P4 + c, *CBc = S.CB + c;
-    const bool mva = a >= 0, mvb = b >= 0;
-    auto inM = [&](int i) { return i == a || (mvb && i == b); };
+    const bool mvb = b >= 0;
+    const bool any_b = __any_sync(FULL, mvb);
+    const float pi_f = 0.5f * h->two_pi;
 
     float d_pw = 0.f, d_pa = 0.f, d_vbx = 0.f, d_vby = 0.f, d_focal = 0.f, d_clr = 0.f, d_surf = 0.f;
 
-    // ---- the moved objects' own rectangles ----------------------------------------------------------
-    float4 box_oa = make_float4(0.f, 0.f, 0.f, 0.f), box_na = box_oa, box_ob = box_oa, box_nb = box_oa;
-    if (mva) {
+    // ---- the moved objects' own rectangles and the clearances with the same INDEX (quirk Q7), one job per
+    //      lane: 0 = object a, 1 = object b, 2 = clearance a, 3 = clearance b --------------------------------
+    for (int job = g; job < 4; job += G) {
+        const bool second = job & 1, isclr = job >= 2;
+        const int m = second ? b : a;
+        const bool valid = m >= 0 && (!isclr || m < C);
+        const int mm = valid ? m : 0;
+        const float4 kb = isclr ? P.clr_box[mm] : P.obj_box[mm];
+        const float v0 = isclr ? P.clr_v0x[mm] : P.obj_v0x[mm];
+        const float4 o = second ? ob : oa, w = second ? nb : na;
+        const float ds = outside_room(box_at(kb, v0, w.x, w.y), h) - outside_room(box_at(kb, v0, o.x, o.y), h);
+        if (valid) {
+            d_surf += ds;
+            if (!isclr) {
+                const float area = P.obj_area[mm];
+                d_focal += w.w - o.w;
+                d_vbx += area * (w.x - o.x);
+                d_vby += area * (w.y - o.y);
+            }
+        }
+    }
+
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 box_oa, box_na, box_ob = zero4, box_nb = zero4;
+    {
         const float4 kb = P.obj_box[a];
         const float v0 = P.obj_v0x[a];
         box_oa = box_at(kb, v0, oa.x, oa.y);
         box_na = box_at(kb, v0, na.x, na.y);
-        if (g == 0) {
-            const float area = P.obj_area[a];
-            d_surf += outside_room(box_na, h) - outside_room(box_oa, h);
-            d_focal += na.w - oa.w;
-            d_vbx += area * (na.x - oa.x);
-            d_vby += area * (na.y - oa.y);
-        }
     }
     if (mvb) {
         const float4 kb = P.obj_box[b];
         const float v0 = P.obj_v0x[b];
         box_ob = box_at(kb, v0, ob.x, ob.y);
         box_nb = box_at(kb, v0, nb.x, nb.y);
-        if (g == 0) {
-            const float area = P.obj_area[b];
-            d_surf += outside_room(box_nb, h) - outside_room(box_ob, h);
-            d_focal += nb.w - ob.w;
-            d_vbx += area * (nb.x - ob.x);
-            d_vby += area * (nb.y - ob.y);
-        }
     }
 
-    MH_PHASE_SYNC(3);
-    // ---- clearances: pairs (k, moved object) for every k; Q7 surface of clearance INDEX a / b ------
-    if (mva) {
-        for (int k = g; k < C; k += G) {
-            const int src = P.clr_src[k];
-            const float4 kb = P.clr_box[k];
-            const float v0 = P.clr_v0x[k];
-            const float4 cb_old = CBc[k * CPW];
-            float4 cb_new = cb_old;
-            if (inM(src)) {
-                const float4 ps = Pc[src * CPW];
-                cb_new = box_at(kb, v0, ps.x, ps.y);
-            }
-            d_clr += overlap(box_na, cb_new) - overlap(box_oa, cb_old);
-            if (mvb) d_clr += overlap(box_nb, cb_new) - overlap(box_ob, cb_old);
-            if (k == a) d_surf += outside_room(box_at(kb, v0, na.x, na.y), h) - outside_room(box_at(kb, v0, oa.x, oa.y), h);
-            if (mvb && k == b) d_surf += outside_room(box_at(kb, v0, nb.x, nb.y), h) - outside_room(box_at(kb, v0, ob.x, ob.y), h);
-        }
-        // ---- clearances sourced at a moved object against every object that did not move -----------
-        for (int which = 0; which < 2; which++) {
-            const int m = which ? b : a;
-            if (m < 0) continue;
-            const int t0 = P.clr_adj_off[m], t1 = P.clr_adj_off[m + 1];
-            const float4 pm = which ? nb : na;
-            for (int t = t0; t < t1; t++) {
-                const int k = P.clr_adj[t];
-                const float4 cb_old = CBc[k * CPW];
-                const float4 cb_new = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
-                for (int i = g; i < n; i += G) {
-                    if (inM(i)) continue;
-                    const float4 q = Pc[i * CPW];
-                    const float4 bi = box_at(P.obj_box[i], P.obj_v0x[i], q.x, q.y);
-                    d_clr += overlap(bi, cb_new) - overlap(bi, cb_old);
-                }
-            }
-        }
+    // ---- every clearance against the moved objects (the clearance itself may have moved with its source:
+    //      S.P4 already holds the proposal, S.CB still the current layout) ----------------------------------
+    for (int k = g; k < C; k += G) {
+        const float4 cb_old = CBc[k * CPW];
+        const float2 ps = *reinterpret_cast<const float2 *>(&Pc[P.clr_src[k] * CPW]);
+        const float4 cb_new = box_at(P.clr_box[k], P.clr_v0x[k], ps.x, ps.y);
+        d_clr += overlap(box_na, cb_new) - overlap(box_oa, cb_old);
+        if (any_b) d_clr += overlap(box_nb, cb_new) - overlap(box_ob, cb_old);
     }
 
-    MH_PHASE_SYNC(3);
-    // ---- relationships that name a moved object: first collect them per lane, then evaluate slot by
-    //      slot, so that the warp pays for the deepest lane queue and not for every loop trip in
-    //      which some lane happens to hold one ------------------------------------------------------------
-    stash.r0 = stash.r1 = stash.r2 = stash.r3 = -1;
+    // ---- relationships that name a moved object (CSR by object; one that names both is taken from a's
+    //      list only), dealt round-robin to the lanes of the group -------------------------------------------
+    stash.r0 = stash.r1 = -1;
     stash.overflow = 0;
-    if (mva) {
-        int nq = 0;
-        for (int r = g; r < R; r += G) {
-            const int4 id = P.rel_idx[r];
-            if (inM(id.x) || inM(id.y) || inM(id.z) || inM(id.w)) {
-                if (nq == 0) stash.r0 = r;
-                else if (nq == 1) stash.r1 = r;
-                else if (nq == 2) stash.r2 = r;
-                else if (nq == 3) stash.r3 = r;
-                else {                                          // rare: evaluate in place, commit recomputes
-                    float pd, pe;
-                    rel_pen<CPW>(P, Pc, r, pd, pe);
-                    const float2 old = D.pr(r, c);
-                    d_pw += pd - old.x;
-                    d_pa += pe - old.y;
-                    stash.overflow = 1;
-                }
-                nq++;
+    {
+        const int ra0 = P.rel_adj_off[a], na_r = P.rel_adj_off[a + 1] - ra0;
+        const int rb0 = mvb ? P.rel_adj_off[b] : 0, nb_r = mvb ? P.rel_adj_off[b + 1] - rb0 : 0;
+        const int tot = na_r + nb_r;
+        const int tmax = __reduce_max_sync(FULL, tot);
+        int slot = 0;
+        for (int t = g; t < tmax; t += G, slot++) {
+            int r = -1;
+            if (t < na_r) {
+                r = P.rel_adj[ra0 + t];
+            } else if (t < tot) {
+                r = P.rel_adj[rb0 + t - na_r];
+                const int4 id = P.rel_idx[r];
+                if (id.x == a || id.y == a || id.z == a || id.w == a) r = -1;
+            }
+            float pd, pe;
+            rel_pen<CPW>(P, Pc, r >= 0 ? r : 0, pd, pe);
+            if (r >= 0) {
+                const float2 old = D.pr(r, c);
+                d_pw += pd - old.x;
+                d_pa += pe - old.y;
+                if (slot == 0) { stash.r0 = r; stash.v0 = make_float2(pd, pe); }
+                else if (slot == 1) { stash.r1 = r; stash.v1 = make_float2(pd, pe); }
+                else stash.overflow = 1;
             }
         }
+        // the commit's recomputation deals the relationships differently: the whole group must take part
+        if (tmax > 2 * G) stash.overflow = -group_min_int<G, kDeltaStr>(-stash.overflow);
     }
-#define MH_REL_SLOT(RQ, VQ)                                   \
-    if (RQ >= 0) {                                            \
-        float pd, pe;                                         \
-        rel_pen<CPW>(P, Pc, RQ, pd, pe);                      \
-        const float2 old = D.pr(RQ, c);                       \
-        d_pw += pd - old.x;                                   \
-        d_pa += pe - old.y;                                   \
-        VQ = make_float2(pd, pe);                             \
-    }
-    MH_REL_SLOT(stash.r0, stash.v0)
-    MH_REL_SLOT(stash.r1, stash.v1)
-    MH_REL_SLOT(stash.r2, stash.v2)
-    MH_REL_SLOT(stash.r3, stash.v3)
-#undef MH_REL_SLOT
 
-    MH_PHASE_SYNC(3);
-    // ---- symmetry: exact memo (sym_memo_eval) ---------------------------------------------------------------
-    const float sym_total = sym_memo_eval<G, kDeltaStr>(P, S, D, c, g, sel, a, b, na, nb);
+    // ---- one pass over the rows that did not move: (i) symmetry -- column update of the row minimum
+    //      (exact: min(old, key(i, a), key(i, b)); a row whose remembered column moved is flagged for a
+    //      rescan); (ii) the row's rectangle against the clearances sourced at a moved object, two such
+    //      clearances per pass (a further pass only if some chain of the warp moved more than two) --------
+    unsigned flags = 0;
+    {
+        const int ca0 = P.clr_adj_off[a], na_c = P.clr_adj_off[a + 1] - ca0;
+        const int cb0 = mvb ? P.clr_adj_off[b] : 0, nb_c = mvb ? P.clr_adj_off[b + 1] - cb0 : 0;
+        const int tot = na_c + nb_c;
+        const int tmax = __reduce_max_sync(FULL, tot);
+        const float4 nbx = mvb ? nb : na;
+        int t0 = 0;
+        do {
+            float4 mo0 = zero4, mn0 = zero4, mo1 = zero4, mn1 = zero4;   // moved clearances: old / new rectangle
+            if (t0 < tot) {
+                const bool fa = t0 < na_c;
+                const int k = P.clr_adj[fa ? ca0 + t0 : cb0 + t0 - na_c];
+                const float4 pm = fa ? na : nb;
+                mo0 = CBc[k * CPW];
+                mn0 = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
+            }
+            if (t0 + 1 < tot) {
+                const bool fa = t0 + 1 < na_c;
+                const int k = P.clr_adj[fa ? ca0 + t0 + 1 : cb0 + t0 + 1 - na_c];
+                const float4 pm = fa ? na : nb;
+                mo1 = CBc[k * CPW];
+                mn1 = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
+            }
+            int p = 0;
+            for (int i = g; i < n; i += G, p++) {
+                const float4 pi = Pc[i * CPW];
+                const bool moved = i == a || i == b;
+                if (t0 == 0 && !moved) {                        // (rows a, b are rescanned below)
+                    const float2 km = D.km(sel, i, c);
+                    float k = km.x;
+                    int arg = __float_as_int(km.y);
+                    const bool hit = arg == a || (mvb && arg == b);
+                    const RowRef rr = sym_row(h, pi);
+                    const float k1 = sym_key(rr, na, pi_f);
+                    if (k1 < k) { k = k1; arg = a; }
+                    if (any_b) {
+                        const float k2 = sym_key(rr, nbx, pi_f);
+                        if (mvb && k2 < k) { k = k2; arg = b; }
+                    }
+                    if (hit) flags |= 1u << p;
+                    else D.km(1 - sel, i, c) = make_float2(k, __int_as_float(arg));
+                }
+                if (tmax > 0) {
+                    const float4 bi = box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y);
+                    float dd = overlap(bi, mn0) - overlap(bi, mo0);
+                    dd += overlap(bi, mn1) - overlap(bi, mo1);
+                    if (!moved) d_clr += dd;
+                }
+            }
+            t0 += 2;
+        } while (t0 < tmax);
+    }
+
+    // ---- rows rescanned by the whole group, two per pass over the columns: first the moved rows, then
+    //      the flagged ones; each group picks its own next rows, the warp pays for the longest queue -------
+    {
+        int row0 = a, row1 = mvb ? b : -1;
+        for (;;) {
+            const RowRef r0 = sym_row(h, Pc[(row0 >= 0 ? row0 : a) * CPW]);   // S.P4 holds the proposal
+            const RowRef r1 = sym_row(h, Pc[(row1 >= 0 ? row1 : a) * CPW]);
+            float k0 = 5.0f, k1 = 5.0f;
+            int a0 = -1, a1 = -1;
+            for (int j = g; j < n; j += G) {
+                const float4 q = Pc[j * CPW];
+                const float x0 = sym_key(r0, q, pi_f), x1 = sym_key(r1, q, pi_f);
+                if (x0 < k0) { k0 = x0; a0 = j; }
+                if (x1 < k1) { k1 = x1; a1 = j; }
+            }
+            group_argmin<G, kDeltaStr>(k0, a0);
+            group_argmin<G, kDeltaStr>(k1, a1);
+            if (g == 0) {
+                if (row0 >= 0) D.km(1 - sel, row0, c) = make_float2(k0, __int_as_float(a0));
+                if (row1 >= 0) D.km(1 - sel, row1, c) = make_float2(k1, __int_as_float(a1));
+            }
+            // next two flagged rows of this group
+            int mine = flags ? g + (__ffs(flags) - 1) * G : 0x7fffffff;
+            row0 = group_min_int<G, kDeltaStr>(mine);
+            if (mine == row0 && mine != 0x7fffffff) flags &= flags - 1;
+            mine = flags ? g + (__ffs(flags) - 1) * G : 0x7fffffff;
+            row1 = group_min_int<G, kDeltaStr>(mine);
+            if (mine == row1 && mine != 0x7fffffff) flags &= flags - 1;
+            if (!__any_sync(FULL, row0 != 0x7fffffff)) break;
+            if (row0 == 0x7fffffff) row0 = -1;
+            if (row1 == 0x7fffffff) row1 = -1;
+        }
+    }
+    __syncwarp();
+    // ---- the symmetry sum, in the row order of the full scan ----------------------------------------------
+    float s = 0.f;
+    for (int i = g; i < n; i += G)
+        s += 5.0f - D.km(1 - sel, i, c).x;
+    const float sym_total = group_sum<G, kDeltaStr>(s);
 
     // ---- totals ---------------------------------------------------------------------------------------
     star.pw = cur.pw + group_sum<G, kDeltaStr>(d_pw);
@@ -372,11 +448,7 @@ __device__ __forceinline__ void delta_commit(const SmemProblem &P, const WarpSta
 {
     using WS = WarpState<G>;
     constexpr int CPW = WS::CPW;
-    const int R = P.h->R;
     const float4 *Pc = S.P4 + c;
-    if (a < 0) return;
-    const bool mvb = b >= 0;
-    auto inM = [&](int i) { return i == a || (mvb && i == b); };
     for (int which = 0; which < 2; which++) {
         const int m = which ? b : a;
         if (m < 0) continue;
@@ -388,12 +460,12 @@ __device__ __forceinline__ void delta_commit(const SmemProblem &P, const WarpSta
     }
     if (stash.r0 >= 0) D.pr(stash.r0, c) = stash.v0;
     if (stash.r1 >= 0) D.pr(stash.r1, c) = stash.v1;
-    if (stash.r2 >= 0) D.pr(stash.r2, c) = stash.v2;
-    if (stash.r3 >= 0) D.pr(stash.r3, c) = stash.v3;
-    if (stash.overflow) {
-        for (int r = g; r < R; r += G) {
-            const int4 id = P.rel_idx[r];
-            if (inM(id.x) || inM(id.y) || inM(id.z) || inM(id.w)) {
+    if (stash.overflow) {                                       // rare: more than 2 G touched relationships
+        for (int which = 0; which < 2; which++) {
+            const int m = which ? b : a;
+            if (m < 0) continue;
+            for (int t = P.rel_adj_off[m] + g; t < P.rel_adj_off[m + 1]; t += G) {
+                const int r = P.rel_adj[t];
                 float pd, pe;
                 rel_pen<CPW>(P, Pc, r, pd, pe);
                 D.pr(r, c) = make_float2(pd, pe);

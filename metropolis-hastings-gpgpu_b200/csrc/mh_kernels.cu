@@ -6,6 +6,7 @@
 //                      Philox proposals, full cost re-evaluation from shared memory, the
 //                      exp(beta dE) accept test, optional best-layout tracking, coalesced
 //                      write-out.  No block-level barrier inside the iteration loop.
+// mh_delta_kernel<G>   the same chain with incremental evaluation (MH_EVAL_DELTA, mh_delta.cuh).
 // mh_score_kernel<G>   all eight cost terms of given layouts (fills resultCosts, which the
 //                      reference forgets -- quirk Q3; also the KernelEvalCosts parity hook).
 // mh_exchange_kernel   replica exchange between neighbouring temperature rungs (extension).
@@ -24,10 +25,7 @@
 
 namespace mh {
 
-#ifndef MH_WARPS_PER_BLOCK
-#define MH_WARPS_PER_BLOCK 4
-#endif
-constexpr int WARPS_PER_BLOCK = MH_WARPS_PER_BLOCK;
+constexpr int WARPS_PER_BLOCK = 4;
 constexpr int THREADS = WARPS_PER_BLOCK * 32;
 #ifndef MH_MEMO_MIN_BLOCKS
 #define MH_MEMO_MIN_BLOCKS 5 // same for the memo / delta forms
@@ -83,11 +81,10 @@ __device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc,
 // MODE 0: every proposal re-evaluates every live cost term from scratch (Kernel.cu:804).
 // MODE 2: the same, except that the O(n^2) symmetry term comes from an exact memo of the row minima
 //         (mh_delta.cuh: sym_memo_eval) -- bit-identical totals, a fraction of the MUFU work.
-// MODE 1: incremental evaluation of every term (mh_delta.cuh: delta_eval), statistically equivalent.
+// (incremental evaluation of every term, MH_EVAL_DELTA, is mh_delta_kernel below)
 template <int G, int MODE>
 __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_MIN_BLOCKS) mh_chain_kernel(const mhLaunch L)
 {
-    constexpr bool DELTA = MODE == 1;
     constexpr bool MEMO = MODE == 2;
     using WS = WarpState<G>;
     using DS = DeltaState<G>;
@@ -99,18 +96,17 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
     const mhProblemHeader *h = P.h;
     const int n = h->n, C = h->C;
 
-    using LM = LaneMap<G, DELTA>;                              // delta mode: interleaved groups
+    using LM = LaneMap<G, false>;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = LM::chain(lane), g = LM::lane_in_group(lane);
     WS S;
     DS D;
     {
-        const int per_warp = WS::words(n, C) + (DELTA ? DS::words(n, h->R, true) : MEMO ? DS::words(n, h->R, false) : 0);
+        const int per_warp = WS::words(n, C) + (MEMO ? DS::words(n, h->R, false) : 0);
         float *base = smem + L.smem_words + warp * per_warp;
         S.bind(base, n, C);
-        if (DELTA || MEMO) D.bind(base + WS::words(n, C), n, h->R);
+        if (MEMO) D.bind(base + WS::words(n, C), n, h->R);
     }
-    RunSums sums = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int sel = 0;
 
     const int chain_raw = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + c;
@@ -137,14 +133,10 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
 
     float cur, best;
     if (L.fresh) {
-        if (DELTA) {
-            cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);
-        } else {
-            RawTerms t;
-            eval_terms<G, false, DELTA>(P, S, c, g, t);
-            cur = combine(h, t).total;                        // Kernel.cu:778
-            if (MEMO) sym_memo_build<G>(P, S, D, c, g, sel);
-        }
+        RawTerms t;
+        eval_terms<G, false>(P, S, c, g, t);
+        cur = combine(h, t).total;                            // Kernel.cu:778
+        if (MEMO) sym_memo_build<G>(P, S, D, c, g, sel);
         best = cur;
         if (L.result_mode == 1) {
             __syncwarp();
@@ -156,7 +148,6 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
     } else {
         cur = L.d_cur_total[chain];
         best = L.d_best_total[chain];
-        if (DELTA) cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);
         if (MEMO) sym_memo_build<G>(P, S, D, c, g, sel);
     }
 
@@ -176,10 +167,6 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
             beta = L.schedule == MH_SCHED_GEOMETRIC ? L.beta_start * exp2f(tt * L.beta_log2_ratio)
                                                     : L.beta_start + (L.beta_end - L.beta_start) * tt;
         }
-
-        if (MODE != 0) MH_PHASE_SYNC(1);
-        if (DELTA && k > 0 && (it % (uint64_t)kRefresh) == 0)   // bound the drift of the running sums
-            cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);
 
         // -- propose (Kernel.cu:576-704): every lane of the group derives the same move -------------
         const Philox4 w = draw_block(L.seed, gchain, it, 0);
@@ -226,38 +213,26 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
         }
         __syncwarp();
 
-        if (MODE != 0) MH_PHASE_SYNC(2);
-        // -- evaluate the proposal (Kernel.cu:804): every live term, from scratch -- or, in delta
-        //    mode, only what the moved objects touch ---------------------------------------------------
+        // -- evaluate the proposal (Kernel.cu:804): every live term, from scratch ---------------------
         float star;
-        RunSums star_sums = sums;
-        RelStash stash;
         const int b_eff = (b == a) ? -1 : b;                    // a swap of an object with itself moves nothing twice
-        if (DELTA) {
-            star = delta_eval<G>(P, S, D, c, g, sel, a, b_eff, oa, ob, na, nb, sums, star_sums, stash);
-        } else if (MEMO) {
+        if (MEMO) {
             RawTerms t;
             eval_terms<G, false, false, true>(P, S, c, g, t);   // every term but symmetry, from scratch
             t.sym = sym_memo_eval<G, false>(P, S, D, c, g, sel, a, b_eff, na, nb);
             star = combine(h, t).total;
         } else {
             RawTerms t;
-            eval_terms<G, false, DELTA>(P, S, c, g, t);
+            eval_terms<G, false>(P, S, c, g, t);
             star = combine(h, t).total;
         }
 
-        if (MODE != 0) MH_PHASE_SYNC(2);
         // -- accept (Kernel.cu:706-713): u < min(1, exp(beta (star - cur))), maximises (Q10) ------
         const float u = uniform01(draw_block(L.seed, gchain, it, 1).x);
         const bool acc = accept_move(u, beta, star, cur);
         __syncwarp();
         if (acc) {
             cur = star;
-            if (DELTA) {
-                sums = star_sums;
-                sel ^= 1;
-                delta_commit<G>(P, S, D, c, g, a, b_eff, stash);
-            }
             if (MEMO) sel ^= 1;
             if (g == 0 && b >= 0 && live) {                    // z, rotX, rotZ travel with the swap: the
                 uint16_t *pm = L.d_perm + (size_t)chain * n;    // permutation lives in global memory, touched
@@ -311,6 +286,218 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
             const int ch = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + cc;
             if (ch < L.n_chains) write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)ch * n, points + (size_t)ch * n, lane);
         }
+    }
+}
+
+// u < min(1, exp(x)), x = beta (star - cur) in double (accept_move), decided from a float estimate of the
+// exponential whenever u is clear of the threshold by more than the estimate's error; the rare
+// in-between case (probability ~2e-4) takes the double-precision exponential.  Same decisions, always.
+__device__ __forceinline__ bool accept_move_fast(float u, float beta, float star, float cur)
+{
+    const float ef = __expf(beta * (star - cur));                // relative error < 4e-5 for |x| <= 100
+    if (u < fminf(1.0f, ef * 0.9999f)) return true;
+    if (u >= ef * 1.0001f) return false;
+    return accept_move(u, beta, star, cur);
+}
+
+// The chain of mh_chain_kernel with incremental evaluation (mh_delta.cuh).  Differences in shape:
+//  * blocks of 4, 8 or 16 warps (blockDim.x; one block per SM at 16) with ONE block barrier per
+//    iteration: the per-iteration code path is longer than the 32 KB instruction cache, and warps that
+//    drift apart evict each other's lines (measured: +60 % at n = 50 with the barrier);
+//  * no branch on the move type: translate / rotate / swap are computed side by side and selected,
+//    so the chains of a warp do not serialise;
+//  * the two Philox blocks of an iteration are computed by different lanes of the group at once.
+template <int G>
+__global__ void __launch_bounds__(512, 1) mh_delta_kernel(const mhLaunch L)
+{
+    using WS = WarpState<G>;
+    using DS = DeltaState<G>;
+    using LM = LaneMap<G, kDeltaStr>;
+    constexpr int CPW = WS::CPW;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) float smem[];
+    const float *gprob = static_cast<const float *>(L.d_problem);
+    stage_problem(smem, gprob, L.smem_words);
+    const SmemProblem P = bind_problem(smem);
+    const mhProblemHeader *h = P.h;
+    const int n = h->n, C = h->C;
+    const int warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = LM::chain(lane), g = LM::lane_in_group(lane);
+    WS S;
+    DS D;
+    {
+        float *base = smem + L.smem_words + warp * (WS::words(n, C) + DS::words(n, h->R, true));
+        S.bind(base, n, C);
+        D.bind(base + WS::words(n, C), n, h->R);
+    }
+    const int chain0 = (blockIdx.x * warps + warp) * CPW;     // first chain of this warp
+    const bool live = chain0 + c < L.n_chains;
+    const int chain = live ? chain0 + c : L.n_chains - 1;     // idle groups shadow the last chain, write nothing
+    const uint64_t gchain = L.chain_offset + (uint64_t)chain * L.chain_stride;
+    const float *cfg0 = gprob + h->off_cfg0;
+    const float *pass = gprob + h->off_pass;
+    PointRec *points = static_cast<PointRec *>(L.d_points);
+
+    for (int i = g; i < n; i += G) {
+        float x, y, r;
+        if (L.fresh) {
+            x = cfg0[i]; y = cfg0[n + i]; r = cfg0[2 * n + i];
+            if (live) L.d_perm[(size_t)chain * n + i] = (uint16_t)i;
+        } else {
+            const size_t o = (size_t)chain * n + i;
+            x = L.d_x[o]; y = L.d_y[o]; r = L.d_rot[o];
+        }
+        S.P4[WS::at(i, c)] = make_float4(x, y, r, focal_cos(h, x, y, r));
+    }
+    __syncwarp();
+
+    RunSums sums;
+    int sel = 0;
+    float cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);   // memo and running sums of the current layout
+    float best = L.fresh ? cur : L.d_best_total[chain];
+    if (L.fresh && L.result_mode == 1) {
+        for (int cc = 0; cc < CPW; cc++)
+            if (chain0 + cc < L.n_chains)
+                write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)(chain0 + cc) * n, points + (size_t)(chain0 + cc) * n, lane);
+    }
+
+    const float room_x0 = h->room_minx, room_y0 = h->room_miny, room_x1 = h->room_maxx, room_y1 = h->room_maxy;
+    const int any_free = h->any_free;
+    TraceRec *trace = static_cast<TraceRec *>(L.d_trace);
+    float beta = L.beta_start;
+    if (L.schedule == MH_SCHED_PER_CHAIN) beta = L.d_beta[chain];
+
+    for (int k = 0; k < L.it_count; k++) {
+        const uint64_t it = L.it_begin + (uint64_t)k;
+        if (L.schedule == MH_SCHED_GEOMETRIC || L.schedule == MH_SCHED_LINEAR) {
+            const int len = L.schedule_length;
+            const uint64_t ic = it < (uint64_t)(len - 1) ? it : (uint64_t)(len - 1);
+            const float tt = len > 1 ? (float)((double)ic / (double)(len - 1)) : 0.f;
+            beta = L.schedule == MH_SCHED_GEOMETRIC ? L.beta_start * exp2f(tt * L.beta_log2_ratio)
+                                                    : L.beta_start + (L.beta_end - L.beta_start) * tt;
+        }
+        if (warps > 4) __syncthreads();                          // keep the block's warps in the same stretch of code
+        if (k > 0 && (it % (uint64_t)kRefresh) == 0)             // bound the drift of the running sums
+            cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);
+
+        // -- random numbers: block 0 (the move) and block 1 (the acceptance uniform) of this iteration --
+        Philox4 w;
+        float u;
+        if (G >= 2) {
+            const Philox4 mine = draw_block(L.seed, gchain, it, (uint32_t)(g & 1));
+            const int l0 = LM::first_lane(c), l1 = l0 + LM::xor_step;   // the group's lanes with g = 0 and g = 1
+            w.x = __shfl_sync(FULL, mine.x, l0);
+            w.y = __shfl_sync(FULL, mine.y, l0);
+            w.z = __shfl_sync(FULL, mine.z, l0);
+            w.w = __shfl_sync(FULL, mine.w, l0);
+            u = uniform01(__shfl_sync(FULL, mine.x, l1));
+        } else {
+            w = draw_block(L.seed, gchain, it, 0);
+            u = uniform01(draw_block(L.seed, gchain, it, 1).x);
+        }
+
+        // -- propose (Kernel.cu:576-704), the three moves side by side ----------------------------------
+        const int p = random_int(uniform01(w.x), 2);
+        int a = -1, b = -1;
+        if (any_free && (p != 2 || n >= 2)) {
+            uint32_t redraw = 2;
+            a = random_int(uniform01(w.y), n - 1);
+            if (p == 2) b = random_int(uniform01(w.z), n - 1);
+            while (P.obj_frozen[a] || (b >= 0 && P.obj_frozen[b])) {            // Kernel.cu:601, 637, 662, 666
+                const Philox4 rw = draw_block(L.seed, gchain, it, redraw++);
+                if (P.obj_frozen[a]) a = random_int(uniform01(rw.x), n - 1);
+                if (b >= 0 && P.obj_frozen[b]) b = random_int(uniform01(rw.y), n - 1);
+            }
+        }
+        const bool moved = a >= 0;
+        const int a_e = moved ? a : 0;                           // no move: "move" object 0 onto itself (all deltas are 0)
+        const float4 oa = S.P4[WS::at(a_e, c)];
+        const float4 ob = S.P4[WS::at(b >= 0 ? b : a_e, c)];
+        float4 na = oa, nb = oa;
+        {
+            float n0, n1;
+            box_muller(w.z, w.w, n0, n1);
+            const float nx = oa.x + n0 * h->std_x, ny = oa.y + n1 * h->std_y;   // translate (Q19), snapped to the room
+            const float tx = nx > room_x1 ? room_x1 : (nx < room_x0 ? room_x0 : nx);
+            const float ty = ny > room_y1 ? room_y1 : (ny < room_y0 ? room_y0 : ny);
+            float ar = oa.z + n0 * h->sigma_t;                                   // rotate, one wrap (Kernel.cu:645-651)
+            if (ar < 0.f) ar += h->two_pi;
+            else if (ar > h->two_pi_cmp) ar -= h->two_pi;
+            if (moved && p == 0) { na.x = tx; na.y = ty; }
+            if (moved && p == 1) na.z = ar;
+            const float fc = focal_cos(h, na.x, na.y, na.z);
+            if (moved && p < 2) na.w = fc;
+            if (p == 2 && moved) { na = ob; nb = oa; }                           // swap (Kernel.cu:675-700)
+        }
+        const int b_eff = (b == a) ? -1 : b;                     // a swap of an object with itself moves nothing twice
+        __syncwarp();
+        if (g == 0 && moved) {
+            S.P4[WS::at(a, c)] = na;
+            if (b >= 0) S.P4[WS::at(b, c)] = nb;
+        }
+        __syncwarp();
+
+        // -- evaluate: only what the moved objects touch --------------------------------------------------
+        RunSums star_sums;
+        RelStash stash;
+        const float star = delta_eval<G>(P, S, D, c, g, sel, a_e, b_eff, oa, ob, na, nb, sums, star_sums, stash);
+
+        // -- accept (Kernel.cu:706-713) -------------------------------------------------------------------
+        const bool acc = accept_move_fast(u, beta, star, cur);
+        __syncwarp();
+        if (acc) {
+            cur = star;
+            sums = star_sums;
+            sel ^= 1;
+            delta_commit<G>(P, S, D, c, g, a_e, b_eff, stash);
+            if (g == 0 && b >= 0 && live) {                      // z, rotX, rotZ travel with the swap
+                uint16_t *pm = L.d_perm + (size_t)chain * n;
+                const uint16_t pa = pm[a];
+                pm[a] = pm[b];
+                pm[b] = pa;
+            }
+        } else if (g == 0 && moved) {
+            S.P4[WS::at(a, c)] = oa;
+            if (b >= 0) S.P4[WS::at(b, c)] = ob;
+        }
+        __syncwarp();
+        if (L.result_mode == 1) {
+            const bool improved = acc && cur > best;
+            if (improved) best = cur;
+            const unsigned mask = __ballot_sync(FULL, improved && live);
+            if (mask) {
+                for (int cc = 0; cc < CPW; cc++)
+                    if (mask & (1u << LM::first_lane(cc)))
+                        write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)(chain0 + cc) * n, points + (size_t)(chain0 + cc) * n, lane);
+            }
+        }
+        if (trace && live && g == 0) {
+            TraceRec r;
+            r.move = p; r.obj1 = a; r.obj2 = b; r.accepted = acc ? 1 : 0;
+            r.star_total = star; r.cur_total = cur; r.u = u; r.beta = beta;
+            trace[(size_t)k * L.n_chains + chain] = r;
+        }
+    }
+
+    __syncwarp();
+    if (live) {
+        for (int i = g; i < n; i += G) {
+            const size_t o = (size_t)chain * n + i;
+            const float4 p = S.P4[WS::at(i, c)];
+            L.d_x[o] = p.x;
+            L.d_y[o] = p.y;
+            L.d_rot[o] = p.z;
+        }
+        if (g == 0) {
+            L.d_cur_total[chain] = cur;
+            L.d_best_total[chain] = best;
+        }
+    }
+    if (L.result_mode == 0) {
+        for (int cc = 0; cc < CPW; cc++)
+            if (chain0 + cc < L.n_chains)
+                write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)(chain0 + cc) * n, points + (size_t)(chain0 + cc) * n, lane);
     }
 }
 
@@ -419,7 +606,7 @@ template <int G, int MODE> static int launch_chains_gm(const mhLaunch &L)
     using WS = WarpState<G>;
     const int chains_per_block = WARPS_PER_BLOCK * WS::CPW;
     const int blocks = (L.n_chains + chains_per_block - 1) / chains_per_block;
-    const int per_warp = WS::words(L.n, L.C) + (MODE == 1 ? DeltaState<G>::words(L.n, L.R, true) : MODE == 2 ? DeltaState<G>::words(L.n, L.R, false) : 0);
+    const int per_warp = WS::words(L.n, L.C) + (MODE == 2 ? DeltaState<G>::words(L.n, L.R, false) : 0);
     const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)WARPS_PER_BLOCK * per_warp);
     cudaError_t e = cudaFuncSetAttribute(mh_chain_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -427,10 +614,23 @@ template <int G, int MODE> static int launch_chains_gm(const mhLaunch &L)
     return (int)cudaGetLastError();
 }
 
+template <int G> static int launch_delta_g(const mhLaunch &L)
+{
+    using WS = WarpState<G>;
+    const int warps = L.warps_per_block == 16 || L.warps_per_block == 8 ? L.warps_per_block : 4;
+    const int chains_per_block = warps * WS::CPW;
+    const int blocks = (L.n_chains + chains_per_block - 1) / chains_per_block;
+    const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)warps * (WS::words(L.n, L.C) + DeltaState<G>::words(L.n, L.R, true)));
+    cudaError_t e = cudaFuncSetAttribute(mh_delta_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    mh_delta_kernel<G><<<blocks, warps * 32, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
+    return (int)cudaGetLastError();
+}
+
 template <int G> static int launch_chains_g(const mhLaunch &L)
 {
     switch (L.eval_mode) {
-    case 1: return launch_chains_gm<G, 1>(L);
+    case 1: return launch_delta_g<G>(L);
     case 2: return launch_chains_gm<G, 2>(L);
     default: return launch_chains_gm<G, 0>(L);
     }
@@ -456,7 +656,7 @@ static int launch_score_g(const void *d_problem, int smem_words, int n, int C, i
 
 extern "C" {
 
-int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int eval_mode)
+int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int eval_mode, int warps)
 {
     int w = 0;
     const bool memo = eval_mode == 1 || eval_mode == 2, pr = eval_mode == 1;
@@ -470,7 +670,8 @@ int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int e
     default: return -1;
     }
     if (memo && (n + lanes - 1) / lanes > 32) return -1; /* the per-lane row flags are one 32-bit word */
-    return 4 * (smem_words + mh::WARPS_PER_BLOCK * w);
+    if (!pr || (warps != 8 && warps != 16)) warps = mh::WARPS_PER_BLOCK;
+    return 4 * (smem_words + warps * w);
 }
 
 int mhdev_launch_chains(const mhLaunch *l)
