@@ -581,6 +581,7 @@ static int launch_segment(mhContext *c, int iterations, void *d_trace)
     L.result_mode = c->opt.result_mode;
     L.eval_mode = c->eval_internal;
     L.warps_per_block = c->delta_warps;
+    L.sync_interval = getenv("MH_DELTA_SYNC") && atoi(getenv("MH_DELTA_SYNC")) > 0 ? atoi(getenv("MH_DELTA_SYNC")) : 1;
     L.beta_start = (float)c->opt.beta_start; L.beta_end = (float)c->opt.beta_end;
     L.beta_log2_ratio = log2f((float)(c->opt.beta_end / c->opt.beta_start));
     L.d_x = c->d_x; L.d_y = c->d_y; L.d_rot = c->d_rot; L.d_perm = c->d_perm; L.d_cur_total = c->d_cur;

@@ -76,7 +76,7 @@ typedef struct mhLaunch {
     float beta_start;
     float beta_end;
     float beta_log2_ratio;  /* log2f(beta_end/beta_start)                                      */
-    float pad;
+    int32_t sync_interval;  /* delta kernel, blocks of 8/16 warps: one block barrier every this many iterations */
     /* chain state, [chain][object] */
     float *d_x, *d_y, *d_rot;
     uint16_t *d_perm;       /* which original object's z/rotX/rotZ sits in slot i (swap moves)  */

@@ -72,6 +72,31 @@ template <int G, bool STR> __device__ __forceinline__ int group_min_int(int v)
     return v;
 }
 
+// Two lexicographic (key, column) minima at once: after the first exchange the lanes with even g carry
+// pair 0 and the lanes with odd g pair 1, so both reductions share one butterfly.  On return lanes with
+// even g hold the group's (k0, a0) and lanes with odd g its (k1, a1); for G = 1 nothing moves.
+template <int G, bool STR> __device__ __forceinline__ void group_argmin2(const int g, float &k0, int &a0, float &k1, int &a1)
+{
+    if (G == 1) return;
+    constexpr int step = LaneMap<G, STR>::xor_step;
+    const bool odd = g & 1;
+    float k = odd ? k1 : k0, sk = odd ? k0 : k1;
+    int arg = odd ? a1 : a0, sa = odd ? a0 : a1;
+    {
+        const float ok = __shfl_xor_sync(0xffffffffu, sk, step);
+        const int oa = __shfl_xor_sync(0xffffffffu, sa, step);
+        if (ok < k || (ok == k && (unsigned)oa < (unsigned)arg)) { k = ok; arg = oa; }
+    }
+#pragma unroll
+    for (int m = 2; m < G; m <<= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, k, m * step);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, m * step);
+        if (ok < k || (ok == k && (unsigned)oa < (unsigned)arg)) { k = ok; arg = oa; }
+    }
+    k0 = k1 = k;
+    a0 = a1 = arg;
+}
+
 // Relationship penalties a proposal recomputed, kept in registers until the accept decision.  The
 // relationships that name a moved object are dealt round-robin to the lanes of the group, so a lane
 // rarely holds more than one; beyond two the commit recomputes.
@@ -366,18 +391,20 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
                     const bool hit = arg == a || (mvb && arg == b);
                     const RowRef rr = sym_row(h, pi);
                     const float k1 = sym_key(rr, na, pi_f);
-                    if (k1 < k) { k = k1; arg = a; }
+                    if (k1 < k || (k1 == k && hit)) { k = k1; arg = a; }
                     if (any_b) {
                         const float k2 = sym_key(rr, nbx, pi_f);
                         if (mvb && k2 < k) { k = k2; arg = b; }
                     }
-                    if (hit) flags |= 1u << p;
+                    // the remembered column moved: if a moved column now does at least as well as the old
+                    // minimum it is the new minimum (every other column is >= the old one); else rescan
+                    if (hit && k == km.x && arg == __float_as_int(km.y)) flags |= 1u << p;
                     else D.km(1 - sel, i, c) = make_float2(k, __int_as_float(arg));
                 }
                 if (tmax > 0) {
                     const float4 bi = box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y);
                     float dd = overlap(bi, mn0) - overlap(bi, mo0);
-                    dd += overlap(bi, mn1) - overlap(bi, mo1);
+                    if (tmax > 1) dd += overlap(bi, mn1) - overlap(bi, mo1);
                     if (!moved) d_clr += dd;
                 }
             }
@@ -385,13 +412,22 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
         } while (t0 < tmax);
     }
 
-    // ---- rows rescanned by the whole group, two per pass over the columns: first the moved rows, then
-    //      the flagged ones; each group picks its own next rows, the warp pays for the longest queue -------
+    // ---- rows rescanned by the whole group, two per pass over the columns: the moved rows first, then
+    //      the flagged ones; each group works through its own queue, the warp pays for the longest --------
     {
-        int row0 = a, row1 = mvb ? b : -1;
+        constexpr int NONE = 0x7fffffff;
+        auto take = [&](bool consume) {                          // next flagged row of this group (NONE: queue empty)
+            const int mine = flags ? g + (__ffs(flags) - 1) * G : NONE;
+            const int row = group_min_int<G, kDeltaStr>(mine);
+            if (consume && mine == row && mine != NONE) flags &= flags - 1;
+            return row;
+        };
+        int row0 = a, row1 = take(!mvb);
+        if (mvb) row1 = b;
         for (;;) {
-            const RowRef r0 = sym_row(h, Pc[(row0 >= 0 ? row0 : a) * CPW]);   // S.P4 holds the proposal
-            const RowRef r1 = sym_row(h, Pc[(row1 >= 0 ? row1 : a) * CPW]);
+            const bool v0 = row0 != NONE, v1 = row1 != NONE;
+            const RowRef r0 = sym_row(h, Pc[(v0 ? row0 : a) * CPW]);   // S.P4 holds the proposal
+            const RowRef r1 = sym_row(h, Pc[(v1 ? row1 : a) * CPW]);
             float k0 = 5.0f, k1 = 5.0f;
             int a0 = -1, a1 = -1;
             for (int j = g; j < n; j += G) {
@@ -400,22 +436,17 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
                 if (x0 < k0) { k0 = x0; a0 = j; }
                 if (x1 < k1) { k1 = x1; a1 = j; }
             }
-            group_argmin<G, kDeltaStr>(k0, a0);
-            group_argmin<G, kDeltaStr>(k1, a1);
-            if (g == 0) {
-                if (row0 >= 0) D.km(1 - sel, row0, c) = make_float2(k0, __int_as_float(a0));
-                if (row1 >= 0) D.km(1 - sel, row1, c) = make_float2(k1, __int_as_float(a1));
+            group_argmin2<G, kDeltaStr>(g, k0, a0, k1, a1);
+            if (G == 1) {
+                if (v0) D.km(1 - sel, row0, c) = make_float2(k0, __int_as_float(a0));
+                if (v1) D.km(1 - sel, row1, c) = make_float2(k1, __int_as_float(a1));
+            } else if (g < 2) {                                  // g = 0 holds row0's minimum, g = 1 row1's
+                const int row = g ? row1 : row0;
+                if (row != NONE) D.km(1 - sel, row, c) = make_float2(k0, __int_as_float(a0));
             }
-            // next two flagged rows of this group
-            int mine = flags ? g + (__ffs(flags) - 1) * G : 0x7fffffff;
-            row0 = group_min_int<G, kDeltaStr>(mine);
-            if (mine == row0 && mine != 0x7fffffff) flags &= flags - 1;
-            mine = flags ? g + (__ffs(flags) - 1) * G : 0x7fffffff;
-            row1 = group_min_int<G, kDeltaStr>(mine);
-            if (mine == row1 && mine != 0x7fffffff) flags &= flags - 1;
-            if (!__any_sync(FULL, row0 != 0x7fffffff)) break;
-            if (row0 == 0x7fffffff) row0 = -1;
-            if (row1 == 0x7fffffff) row1 = -1;
+            row0 = take(true);
+            row1 = take(true);
+            if (!__any_sync(FULL, row0 != NONE)) break;
         }
     }
     __syncwarp();

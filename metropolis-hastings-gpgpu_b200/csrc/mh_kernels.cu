@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(512, 1) mh_delta_kernel(const mhLaunch L)
             beta = L.schedule == MH_SCHED_GEOMETRIC ? L.beta_start * exp2f(tt * L.beta_log2_ratio)
                                                     : L.beta_start + (L.beta_end - L.beta_start) * tt;
         }
-        if (warps > 4) __syncthreads();                          // keep the block's warps in the same stretch of code
+        if (warps > 4 && (k % L.sync_interval) == 0) __syncthreads();   // keep the block's warps in the same stretch of code
         if (k > 0 && (it % (uint64_t)kRefresh) == 0)             // bound the drift of the running sums
             cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);
 
