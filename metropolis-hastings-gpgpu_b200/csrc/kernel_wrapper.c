@@ -351,9 +351,9 @@ static int choose_lanes(int n, int C, int R, int smem_words, int n_chains, int r
  * Its per-proposal work is ~(fixed scalar part) + (3n + 2C)/G pair evaluations per lane, and the fixed
  * part is repeated by every lane of a group, so narrow groups win as long as a lane keeps 6-8 rows
  * (measured on B200: n=8 -> 1, n=16 -> 2, n=50 -> 8, n=200 -> 32 lanes).  Few chains: widen the groups
- * until the machine is covered.  Blocks of 8 warps (two per SM, with the per-iteration barrier that keeps
- * their instruction fetch together) when shared memory allows and the grid still covers the SMs. */
-static int choose_delta_shape(int n, int C, int R, int smem_words, int n_chains, int requested, int *lanes_out, int *warps_out)
+ * until the machine is covered.  Blocks of 8 warps when shared memory allows and the grid still covers
+ * the SMs (the problem blob is staged once per block: 8 >= 4 at n = 50, +20 % at n = 200). */
+static int choose_delta_shape(int n, int C, int R, int smem_words, int n_chains, int requested, int eval_mode, int *lanes_out, int *warps_out)
 {
     int max_block = 0, max_sm = 0, sms = 0;
     int e = mhdev_device_limits(&max_block, &max_sm, &sms, NULL, NULL, NULL, NULL, 0);
@@ -366,16 +366,16 @@ static int choose_delta_shape(int n, int C, int R, int smem_words, int n_chains,
     if (requested > 0) G = requested;
     for (;; G *= 2) {                                                       /* must fit with 4 warps per block */
         if (G > 32) { snprintf(g_err, sizeof g_err, "problem does not fit in shared memory (n=%d, C=%d, delta evaluation)", n, C); return -1; }
-        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, MH_EVAL_DELTA, 4);
+        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, eval_mode, 4);
         if (bytes >= 0 && bytes <= max_block) break;
         if (requested > 0) { snprintf(g_err, sizeof g_err, "lanes_per_chain=%d does not fit in shared memory (delta evaluation)", G); return -1; }
     }
-    int warps = 8;                                                          /* measured: 8 >= 16 > 4 at n = 50 and n = 200 */
+    int warps = 8;
     const char *wenv = getenv("MH_DELTA_WARPS");
-    if (wenv) warps = atoi(wenv) >= 16 ? 16 : atoi(wenv) >= 8 ? 8 : 4;
+    if (wenv) warps = atoi(wenv) >= 8 ? 8 : 4;
     const double total_warps = ceil((double)n_chains * G / 32.0);
     while (warps > 4) {
-        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, MH_EVAL_DELTA, warps);
+        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, eval_mode, warps);
         if (bytes >= 0 && bytes <= max_block && (wenv || total_warps / warps >= (double)sms)) break;
         warps /= 2;
     }
@@ -493,13 +493,15 @@ MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationship
     c->lanes = -1;
     if (c->opt.eval_mode == MH_EVAL_FULL && c->n >= MH_MEMO_MIN_OBJS && !getenv("MH_FULL_SCAN")) {
         /* bit-identical and faster from ~64 objects up (measured: +9% at 64, +33% at 100, +86% at 200) */
-        c->lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, MH_EVAL_MEMO);
-        if (c->lanes > 0) c->eval_internal = MH_EVAL_MEMO;
+        if (choose_delta_shape(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, MH_EVAL_MEMO, &c->lanes, &c->delta_warps) == 0)
+            c->eval_internal = MH_EVAL_MEMO;
+        else
+            c->lanes = -1;                                   /* does not fit: the plain scan needs less shared memory */
         g_err[0] = 0;
+    } else if (c->eval_internal == MH_EVAL_DELTA || c->eval_internal == MH_EVAL_MEMO) {
+        if (choose_delta_shape(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, c->eval_internal, &c->lanes, &c->delta_warps)) goto fail;
     }
-    if (c->eval_internal == MH_EVAL_DELTA) {
-        if (choose_delta_shape(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, &c->lanes, &c->delta_warps)) goto fail;
-    } else if (c->lanes < 0) {
+    if (c->lanes < 0) {
         c->lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, c->eval_internal);
     }
     if (c->lanes < 0) goto fail;
@@ -581,7 +583,6 @@ static int launch_segment(mhContext *c, int iterations, void *d_trace)
     L.result_mode = c->opt.result_mode;
     L.eval_mode = c->eval_internal;
     L.warps_per_block = c->delta_warps;
-    L.sync_interval = getenv("MH_DELTA_SYNC") && atoi(getenv("MH_DELTA_SYNC")) > 0 ? atoi(getenv("MH_DELTA_SYNC")) : 1;
     L.beta_start = (float)c->opt.beta_start; L.beta_end = (float)c->opt.beta_end;
     L.beta_log2_ratio = log2f((float)(c->opt.beta_end / c->opt.beta_start));
     L.d_x = c->d_x; L.d_y = c->d_y; L.d_rot = c->d_rot; L.d_perm = c->d_perm; L.d_cur_total = c->d_cur;

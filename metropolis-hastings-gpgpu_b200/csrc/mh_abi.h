@@ -72,11 +72,11 @@ typedef struct mhLaunch {
     int32_t schedule_length;
     int32_t result_mode;    /* 0 final layout, 1 best layout                                   */
     int32_t eval_mode;      /* 0 full re-evaluation per proposal, 1 delta evaluation            */
-    int32_t warps_per_block; /* delta kernel only: 4, 8 or 16 (the other forms are compiled for 4) */
+    int32_t warps_per_block; /* delta kernel only: 4 or 8 (the other forms are compiled for 4) */
     float beta_start;
     float beta_end;
     float beta_log2_ratio;  /* log2f(beta_end/beta_start)                                      */
-    int32_t sync_interval;  /* delta kernel, blocks of 8/16 warps: one block barrier every this many iterations */
+    float pad;
     /* chain state, [chain][object] */
     float *d_x, *d_y, *d_rot;
     uint16_t *d_perm;       /* which original object's z/rotX/rotZ sits in slot i (swap moves)  */

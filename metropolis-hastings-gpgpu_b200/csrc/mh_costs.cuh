@@ -279,7 +279,7 @@ __device__ __forceinline__ void rel_pen(const SmemProblem &P, const float4 *Pc, 
 
 // All terms of one layout.  Every lane of the warp must call this (it synchronises the warp);
 // on return every lane of a group holds the group's totals.
-template <int G, bool WITH_OFFLIMITS, bool STR = false, bool SKIP_SYM = false>
+template <int G, bool WITH_OFFLIMITS, bool STR = false, bool SKIP_SYM = false, bool SKIP_REL = false>
 __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState<G> &S, const int c, const int g, RawTerms &t)
 {
     using WS = WarpState<G>;
@@ -428,15 +428,17 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
     }
 
     // ---- relationships --------------------------------------------------------------------------
-    for (int r = g; r < R; r += G) {
-        float pd, pe;
-        rel_pen<CPW>(P, Pc, r, pd, pe);
-        pw += pd;
-        pa += pe;
+    if (!SKIP_REL) {
+        for (int r = g; r < R; r += G) {
+            float pd, pe;
+            rel_pen<CPW>(P, Pc, r, pd, pe);
+            pw += pd;
+            pa += pe;
+        }
     }
 
-    t.pw = group_sum<G, STR>(pw);
-    t.pa = group_sum<G, STR>(pa);
+    t.pw = SKIP_REL ? 0.f : group_sum<G, STR>(pw);
+    t.pa = SKIP_REL ? 0.f : group_sum<G, STR>(pa);
     t.vbx = group_sum<G, STR>(vbx);
     t.vby = group_sum<G, STR>(vby);
     t.focal = group_sum<G, STR>(focal);

@@ -24,6 +24,10 @@
 
 namespace mh {
 
+// The loops of delta_eval are deliberately NOT unrolled: the kernel's per-iteration code path must stay
+// inside the 32 KB instruction cache (measured at n = 50: 8.4e8 proposals/s rolled against 7.2e8 with
+// the compiler's 4x unrolling -- with the unrolled code the warps of an SM evict each other's lines).
+constexpr int kDuClr = 1, kDuRow = 1, kDuScan = 1, kDuSum = 1;
 constexpr int kRefresh = 128; // iterations between full rebuilds of the memo and the running sums
 
 template <int G> struct DeltaState {
@@ -139,86 +143,86 @@ __device__ __forceinline__ void sym_memo_build(const SmemProblem &P, const WarpS
     __syncwarp();
 }
 
-// Symmetry term of the proposal that moved objects a and b (-1 = none) to na / nb (S.P4 already holds
-// them), from the memo of the current layout in KM[sel]; writes the proposal's memo to KM[1-sel] and
-// returns sum_i (5 - min_j key(i,j)) reduced over the group.  The row minima are EXACT (min is exact),
-// and each lane adds its rows in increasing row order, exactly as the full scan of eval_terms does, so
-// the value is bit-identical to a full evaluation.  Every lane of the warp must call this.
-template <int G, bool STR>
-__device__ __forceinline__ float sym_memo_eval(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, const int c, const int g,
-                                               const int sel, const int a, const int b, const float4 na, const float4 nb)
+// Column update of row i (an object that did not move) for the proposal that moved columns a and b
+// (b = a's duplicate when only one moved): the row minimum becomes min(old, key(i, a), key(i, b)) -- exact,
+// since every other column is unchanged -- unless the remembered column itself moved and neither moved
+// column does at least as well as the old minimum: then the row is flagged (bit p) for a rescan.
+template <int G>
+__device__ __forceinline__ void sym_col_update(const mhProblemHeader *h, const DeltaState<G> &D, const int c, const int sel, const int i,
+                                               const int p, const float4 pi, const int a, const int b, const bool mvb, const bool any_b,
+                                               const float4 na, const float4 nbx, const float pi_f, unsigned &flags)
+{
+    const float2 km = D.km(sel, i, c);
+    float k = km.x;
+    int arg = __float_as_int(km.y);
+    const bool hit = arg == a || (mvb && arg == b);
+    const RowRef rr = sym_row(h, pi);
+    const float k1 = sym_key(rr, na, pi_f);
+    if (k1 < k || (k1 == k && hit)) { k = k1; arg = a; }
+    if (any_b) {
+        const float k2 = sym_key(rr, nbx, pi_f);
+        if (mvb && k2 < k) { k = k2; arg = b; }
+    }
+    if (hit && k == km.x && arg == __float_as_int(km.y)) flags |= 1u << p;
+    else D.km(1 - sel, i, c) = make_float2(k, __int_as_float(arg));
+}
+
+// Rows rescanned by the whole group, two per pass over the columns: the moved rows first, then the
+// flagged ones; each group works through its own queue, the warp pays for the longest.  Then the
+// symmetry sum of the proposal's memo (buffer 1-sel), each lane adding its rows in the order of the full
+// scan, so that the value is bit-identical to eval_terms' (min is exact).  Every lane of the warp must
+// call this; S.P4 holds the proposal.
+template <int G>
+__device__ __forceinline__ float sym_rescan_sum(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, const int c, const int g,
+                                                const int sel, const int a, const int b, unsigned flags)
 {
     constexpr int CPW = WarpState<G>::CPW;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NONE = 0x7fffffff;
     const mhProblemHeader *h = P.h;
     const int n = h->n;
     const float pi_f = 0.5f * h->two_pi;
     const float4 *Pc = S.P4 + c;
-    const bool mva = a >= 0, mvb = b >= 0;
-    auto inM = [&](int i) { return i == a || (mvb && i == b); };
-
-    // ---- column update of the rows that did not move ---------------------------------------------------
-    unsigned flags = 0;
-    {
-        int p = 0;
-        for (int i = g; i < n; i += G, p++) {
-            if (mva && inM(i)) continue;                        // rescanned below
-            const float2 km = D.km(sel, i, c);
-            float k = km.x;
-            int arg = __float_as_int(km.y);
-            if (mva) {
-                if (arg == a || (mvb && arg == b)) {            // the remembered best column moved
-                    flags |= 1u << p;
-                    continue;
-                }
-                const RowRef rr = sym_row(h, Pc[i * CPW]);
-                const float k1 = sym_key(rr, na, pi_f);
-                if (k1 < k) { k = k1; arg = a; }
-                if (mvb) {
-                    const float k2 = sym_key(rr, nb, pi_f);
-                    if (k2 < k) { k = k2; arg = b; }
-                }
-            }
-            D.km(1 - sel, i, c) = make_float2(k, __int_as_float(arg));
-        }
-    }
-    // ---- rows rescanned by the whole group.  The moved rows a and b share one pass over the columns;
-    //      rows whose remembered column moved are taken one per trip, each group picking its own next
-    //      row, so the warp pays for the longest group queue. -----------------------------------------------
-    if (__any_sync(0xffffffffu, mva)) {
-        const RowRef ra = sym_row(h, mva ? na : Pc[0]), rb = sym_row(h, mvb ? nb : Pc[0]);
-        float ka = 5.0f, kb2 = 5.0f;
-        int aa = -1, ab = -1;
+    const bool mvb = b >= 0;
+    auto take = [&](bool consume) {                              // next flagged row of this group (NONE: queue empty)
+        const int mine = flags ? g + (__ffs(flags) - 1) * G : NONE;
+        const int row = group_min_int<G, kDeltaStr>(mine);
+        if (consume && mine == row && mine != NONE) flags &= flags - 1;
+        return row;
+    };
+    int row0 = a, row1 = take(!mvb);
+    if (mvb) row1 = b;
+    for (;;) {
+        const bool v0 = row0 != NONE, v1 = row1 != NONE;
+        const RowRef r0 = sym_row(h, Pc[(v0 ? row0 : a) * CPW]);
+        const RowRef r1 = sym_row(h, Pc[(v1 ? row1 : a) * CPW]);
+        float k0 = 5.0f, k1 = 5.0f;
+        int a0 = -1, a1 = -1;
+#pragma unroll kDuScan
         for (int j = g; j < n; j += G) {
             const float4 q = Pc[j * CPW];
-            const float k1 = sym_key(ra, q, pi_f), k2 = sym_key(rb, q, pi_f);
-            if (k1 < ka) { ka = k1; aa = j; }
-            if (k2 < kb2) { kb2 = k2; ab = j; }
+            const float x0 = sym_key(r0, q, pi_f), x1 = sym_key(r1, q, pi_f);
+            if (x0 < k0) { k0 = x0; a0 = j; }
+            if (x1 < k1) { k1 = x1; a1 = j; }
         }
-        group_argmin<G, STR>(ka, aa);
-        group_argmin<G, STR>(kb2, ab);
-        if (g == 0) {
-            if (mva) D.km(1 - sel, a, c) = make_float2(ka, __int_as_float(aa));
-            if (mvb) D.km(1 - sel, b, c) = make_float2(kb2, __int_as_float(ab));
+        group_argmin2<G, kDeltaStr>(g, k0, a0, k1, a1);
+        if (G == 1) {
+            if (v0) D.km(1 - sel, row0, c) = make_float2(k0, __int_as_float(a0));
+            if (v1) D.km(1 - sel, row1, c) = make_float2(k1, __int_as_float(a1));
+        } else if (g < 2) {                                      // g = 0 holds row0's minimum, g = 1 row1's
+            const int row = g ? row1 : row0;
+            if (row != NONE) D.km(1 - sel, row, c) = make_float2(k0, __int_as_float(a0));
         }
-    }
-    for (;;) {
-        const int mine = flags ? g + (__ffs(flags) - 1) * G : 0x7fffffff;
-        const int row = group_min_int<G, STR>(mine);
-        if (!__any_sync(0xffffffffu, row != 0x7fffffff)) break;
-        const bool act = row != 0x7fffffff;
-        if (act && mine == row) flags &= flags - 1;
-        float k;
-        int arg;
-        sym_scan<CPW>(sym_row(h, Pc[(act ? row : 0) * CPW]), Pc, n, g, G, pi_f, k, arg);
-        group_argmin<G, STR>(k, arg);
-        if (act && g == 0) D.km(1 - sel, row, c) = make_float2(k, __int_as_float(arg));
+        row0 = take(true);
+        row1 = take(true);
+        if (!__any_sync(FULL, row0 != NONE)) break;
     }
     __syncwarp();
-    // ---- the sum, in the row order of the full scan --------------------------------------------------------
     float s = 0.f;
+#pragma unroll kDuSum
     for (int i = g; i < n; i += G)
         s += 5.0f - D.km(1 - sel, i, c).x;
-    return group_sum<G, STR>(s);
+    return group_sum<G, kDeltaStr>(s);
 }
 
 // Rebuild the memo and the running sums of the CURRENT layout from scratch; returns its total.
@@ -310,6 +314,7 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
 
     // ---- every clearance against the moved objects (the clearance itself may have moved with its source:
     //      S.P4 already holds the proposal, S.CB still the current layout) ----------------------------------
+#pragma unroll kDuClr
     for (int k = g; k < C; k += G) {
         const float4 cb_old = CBc[k * CPW];
         const float2 ps = *reinterpret_cast<const float2 *>(&Pc[P.clr_src[k] * CPW]);
@@ -381,26 +386,12 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
                 mn1 = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
             }
             int p = 0;
+#pragma unroll kDuRow
             for (int i = g; i < n; i += G, p++) {
                 const float4 pi = Pc[i * CPW];
                 const bool moved = i == a || i == b;
-                if (t0 == 0 && !moved) {                        // (rows a, b are rescanned below)
-                    const float2 km = D.km(sel, i, c);
-                    float k = km.x;
-                    int arg = __float_as_int(km.y);
-                    const bool hit = arg == a || (mvb && arg == b);
-                    const RowRef rr = sym_row(h, pi);
-                    const float k1 = sym_key(rr, na, pi_f);
-                    if (k1 < k || (k1 == k && hit)) { k = k1; arg = a; }
-                    if (any_b) {
-                        const float k2 = sym_key(rr, nbx, pi_f);
-                        if (mvb && k2 < k) { k = k2; arg = b; }
-                    }
-                    // the remembered column moved: if a moved column now does at least as well as the old
-                    // minimum it is the new minimum (every other column is >= the old one); else rescan
-                    if (hit && k == km.x && arg == __float_as_int(km.y)) flags |= 1u << p;
-                    else D.km(1 - sel, i, c) = make_float2(k, __int_as_float(arg));
-                }
+                if (t0 == 0 && !moved)                          // (rows a, b are rescanned below)
+                    sym_col_update<G>(h, D, c, sel, i, p, pi, a, b, mvb, any_b, na, nbx, pi_f, flags);
                 if (tmax > 0) {
                     const float4 bi = box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y);
                     float dd = overlap(bi, mn0) - overlap(bi, mo0);
@@ -412,49 +403,8 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
         } while (t0 < tmax);
     }
 
-    // ---- rows rescanned by the whole group, two per pass over the columns: the moved rows first, then
-    //      the flagged ones; each group works through its own queue, the warp pays for the longest --------
-    {
-        constexpr int NONE = 0x7fffffff;
-        auto take = [&](bool consume) {                          // next flagged row of this group (NONE: queue empty)
-            const int mine = flags ? g + (__ffs(flags) - 1) * G : NONE;
-            const int row = group_min_int<G, kDeltaStr>(mine);
-            if (consume && mine == row && mine != NONE) flags &= flags - 1;
-            return row;
-        };
-        int row0 = a, row1 = take(!mvb);
-        if (mvb) row1 = b;
-        for (;;) {
-            const bool v0 = row0 != NONE, v1 = row1 != NONE;
-            const RowRef r0 = sym_row(h, Pc[(v0 ? row0 : a) * CPW]);   // S.P4 holds the proposal
-            const RowRef r1 = sym_row(h, Pc[(v1 ? row1 : a) * CPW]);
-            float k0 = 5.0f, k1 = 5.0f;
-            int a0 = -1, a1 = -1;
-            for (int j = g; j < n; j += G) {
-                const float4 q = Pc[j * CPW];
-                const float x0 = sym_key(r0, q, pi_f), x1 = sym_key(r1, q, pi_f);
-                if (x0 < k0) { k0 = x0; a0 = j; }
-                if (x1 < k1) { k1 = x1; a1 = j; }
-            }
-            group_argmin2<G, kDeltaStr>(g, k0, a0, k1, a1);
-            if (G == 1) {
-                if (v0) D.km(1 - sel, row0, c) = make_float2(k0, __int_as_float(a0));
-                if (v1) D.km(1 - sel, row1, c) = make_float2(k1, __int_as_float(a1));
-            } else if (g < 2) {                                  // g = 0 holds row0's minimum, g = 1 row1's
-                const int row = g ? row1 : row0;
-                if (row != NONE) D.km(1 - sel, row, c) = make_float2(k0, __int_as_float(a0));
-            }
-            row0 = take(true);
-            row1 = take(true);
-            if (!__any_sync(FULL, row0 != NONE)) break;
-        }
-    }
-    __syncwarp();
-    // ---- the symmetry sum, in the row order of the full scan ----------------------------------------------
-    float s = 0.f;
-    for (int i = g; i < n; i += G)
-        s += 5.0f - D.km(1 - sel, i, c).x;
-    const float sym_total = group_sum<G, kDeltaStr>(s);
+    // ---- symmetry: rescans of the moved and the flagged rows, then the sum ------------------------------
+    const float sym_total = sym_rescan_sum<G>(P, S, D, c, g, sel, a, b, flags);
 
     // ---- totals ---------------------------------------------------------------------------------------
     star.pw = cur.pw + group_sum<G, kDeltaStr>(d_pw);
@@ -492,6 +442,114 @@ __device__ __forceinline__ void delta_commit(const SmemProblem &P, const WarpSta
     if (stash.r0 >= 0) D.pr(stash.r0, c) = stash.v0;
     if (stash.r1 >= 0) D.pr(stash.r1, c) = stash.v1;
     if (stash.overflow) {                                       // rare: more than 2 G touched relationships
+        for (int which = 0; which < 2; which++) {
+            const int m = which ? b : a;
+            if (m < 0) continue;
+            for (int t = P.rel_adj_off[m] + g; t < P.rel_adj_off[m + 1]; t += G) {
+                const int r = P.rel_adj[t];
+                float pd, pe;
+                rel_pen<CPW>(P, Pc, r, pd, pe);
+                D.pr(r, c) = make_float2(pd, pe);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MH_EVAL_MEMO: full evaluation, bit for bit, at a fraction of the work.  Every term of the proposal is
+// what eval_terms computes for it -- same values, added in the same order:
+//   symmetry       the exact memo above (row minima; min is exact);
+//   relationships  only those that name a moved object are recomputed (into the PR memo); every lane
+//                  then adds ITS relationships r = g, g+G, ... from the memo, as eval_terms does;
+//   the rest       (clearance, surface, visual balance, focal) from scratch by eval_terms itself.
+// Nothing is a running sum, so nothing drifts and there is no periodic rebuild.
+struct ExactStash {
+    int r0, r1;      // relationships this lane overwrote in the PR memo ...
+    float2 o0, o1;   // ... and their penalties in the current layout (restored on rejection)
+    int overflow;    // some lane of the group overwrote more than two: rejection recomputes
+};
+
+template <int G>
+__device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, const int c, const int g,
+                                            const int sel, const int a, const int b, const float4 na, const float4 nb, ExactStash &stash)
+{
+    using WS = WarpState<G>;
+    constexpr int CPW = WS::CPW;
+    constexpr unsigned FULL = 0xffffffffu;
+    const mhProblemHeader *h = P.h;
+    const int n = h->n, R = h->R;
+    const float4 *Pc = S.P4 + c;
+    const bool mvb = b >= 0;
+    const bool any_b = __any_sync(FULL, mvb);
+    const float pi_f = 0.5f * h->two_pi;
+
+    RawTerms t;
+    eval_terms<G, false, kDeltaStr, true, true>(P, S, c, g, t);   // every term but symmetry and relationships
+
+    stash.r0 = stash.r1 = -1;
+    stash.overflow = 0;
+    {
+        const int ra0 = P.rel_adj_off[a], na_r = P.rel_adj_off[a + 1] - ra0;
+        const int rb0 = mvb ? P.rel_adj_off[b] : 0, nb_r = mvb ? P.rel_adj_off[b + 1] - rb0 : 0;
+        const int tot = na_r + nb_r;
+        const int tmax = __reduce_max_sync(FULL, tot);
+        int slot = 0;
+        for (int tt = g; tt < tmax; tt += G, slot++) {
+            int r = -1;
+            if (tt < na_r) {
+                r = P.rel_adj[ra0 + tt];
+            } else if (tt < tot) {
+                r = P.rel_adj[rb0 + tt - na_r];
+                const int4 id = P.rel_idx[r];
+                if (id.x == a || id.y == a || id.z == a || id.w == a) r = -1;
+            }
+            float pd, pe;
+            rel_pen<CPW>(P, Pc, r >= 0 ? r : 0, pd, pe);
+            if (r >= 0) {
+                const float2 old = D.pr(r, c);
+                D.pr(r, c) = make_float2(pd, pe);
+                if (slot == 0) { stash.r0 = r; stash.o0 = old; }
+                else if (slot == 1) { stash.r1 = r; stash.o1 = old; }
+                else stash.overflow = 1;
+            }
+        }
+        if (tmax > 2 * G) stash.overflow = -group_min_int<G, kDeltaStr>(-stash.overflow);
+    }
+    __syncwarp();
+    {
+        float pw = 0.f, pa = 0.f;
+#pragma unroll kDuSum
+        for (int r = g; r < R; r += G) {
+            const float2 v = D.pr(r, c);
+            pw += v.x;
+            pa += v.y;
+        }
+        t.pw = group_sum<G, kDeltaStr>(pw);
+        t.pa = group_sum<G, kDeltaStr>(pa);
+    }
+
+    unsigned flags = 0;
+    {
+        const float4 nbx = mvb ? nb : na;
+        int p = 0;
+#pragma unroll kDuRow
+        for (int i = g; i < n; i += G, p++)
+            if (i != a && i != b) sym_col_update<G>(h, D, c, sel, i, p, Pc[i * CPW], a, b, mvb, any_b, na, nbx, pi_f, flags);
+    }
+    t.sym = sym_rescan_sum<G>(P, S, D, c, g, sel, a, b, flags);
+    return combine(h, t).total;
+}
+
+// The proposal was rejected (S.P4 is restored): put the relationship memo back.
+template <int G>
+__device__ __forceinline__ void exact_reject(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, const int c, const int g,
+                                             const int a, const int b, const ExactStash &stash)
+{
+    constexpr int CPW = WarpState<G>::CPW;
+    const float4 *Pc = S.P4 + c;
+    if (stash.r0 >= 0) D.pr(stash.r0, c) = stash.o0;
+    if (stash.r1 >= 0) D.pr(stash.r1, c) = stash.o1;
+    if (stash.overflow) {
         for (int which = 0; which < 2; which++) {
             const int m = which ? b : a;
             if (m < 0) continue;

@@ -27,9 +27,6 @@ namespace mh {
 
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int THREADS = WARPS_PER_BLOCK * 32;
-#ifndef MH_MEMO_MIN_BLOCKS
-#define MH_MEMO_MIN_BLOCKS 5 // same for the memo / delta forms
-#endif
 #ifndef MH_MIN_BLOCKS
 #define MH_MIN_BLOCKS 5 // resident 128-thread blocks per SM the chain kernel is compiled for (<= 96 registers; 6 blocks = 80 registers measured slower)
 #endif
@@ -78,16 +75,13 @@ __device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc,
     }
 }
 
-// MODE 0: every proposal re-evaluates every live cost term from scratch (Kernel.cu:804).
-// MODE 2: the same, except that the O(n^2) symmetry term comes from an exact memo of the row minima
-//         (mh_delta.cuh: sym_memo_eval) -- bit-identical totals, a fraction of the MUFU work.
-// (incremental evaluation of every term, MH_EVAL_DELTA, is mh_delta_kernel below)
-template <int G, int MODE>
-__global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_MIN_BLOCKS) mh_chain_kernel(const mhLaunch L)
+// Every proposal re-evaluates every live cost term from scratch (Kernel.cu:804).  (The forms that do
+// less work for the same or a statistically equivalent result, MH_EVAL_MEMO and MH_EVAL_DELTA, are
+// mh_delta_kernel below.)
+template <int G>
+__global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const mhLaunch L)
 {
-    constexpr bool MEMO = MODE == 2;
     using WS = WarpState<G>;
-    using DS = DeltaState<G>;
     constexpr int CPW = WS::CPW;
     extern __shared__ __align__(16) float smem[];
     const float *gprob = static_cast<const float *>(L.d_problem);
@@ -100,14 +94,7 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = LM::chain(lane), g = LM::lane_in_group(lane);
     WS S;
-    DS D;
-    {
-        const int per_warp = WS::words(n, C) + (MEMO ? DS::words(n, h->R, false) : 0);
-        float *base = smem + L.smem_words + warp * per_warp;
-        S.bind(base, n, C);
-        if (MEMO) D.bind(base + WS::words(n, C), n, h->R);
-    }
-    int sel = 0;
+    S.bind(smem + L.smem_words + warp * WS::words(n, C), n, C);
 
     const int chain_raw = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + c;
     const bool live = chain_raw < L.n_chains;
@@ -136,7 +123,6 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
         RawTerms t;
         eval_terms<G, false>(P, S, c, g, t);
         cur = combine(h, t).total;                            // Kernel.cu:778
-        if (MEMO) sym_memo_build<G>(P, S, D, c, g, sel);
         best = cur;
         if (L.result_mode == 1) {
             __syncwarp();
@@ -148,7 +134,6 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
     } else {
         cur = L.d_cur_total[chain];
         best = L.d_best_total[chain];
-        if (MEMO) sym_memo_build<G>(P, S, D, c, g, sel);
     }
 
     const float room_x0 = h->room_minx, room_y0 = h->room_miny, room_x1 = h->room_maxx, room_y1 = h->room_maxy;
@@ -215,13 +200,7 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
 
         // -- evaluate the proposal (Kernel.cu:804): every live term, from scratch ---------------------
         float star;
-        const int b_eff = (b == a) ? -1 : b;                    // a swap of an object with itself moves nothing twice
-        if (MEMO) {
-            RawTerms t;
-            eval_terms<G, false, false, true>(P, S, c, g, t);   // every term but symmetry, from scratch
-            t.sym = sym_memo_eval<G, false>(P, S, D, c, g, sel, a, b_eff, na, nb);
-            star = combine(h, t).total;
-        } else {
+        {
             RawTerms t;
             eval_terms<G, false>(P, S, c, g, t);
             star = combine(h, t).total;
@@ -233,7 +212,6 @@ __global__ void __launch_bounds__(THREADS, MODE == 0 ? MH_MIN_BLOCKS : MH_MEMO_M
         __syncwarp();
         if (acc) {
             cur = star;
-            if (MEMO) sel ^= 1;
             if (g == 0 && b >= 0 && live) {                    // z, rotX, rotZ travel with the swap: the
                 uint16_t *pm = L.d_perm + (size_t)chain * n;    // permutation lives in global memory, touched
                 const uint16_t pa = pm[a];                      // only by accepted swaps and by the write-out
@@ -301,14 +279,18 @@ __device__ __forceinline__ bool accept_move_fast(float u, float beta, float star
 }
 
 // The chain of mh_chain_kernel with incremental evaluation (mh_delta.cuh).  Differences in shape:
-//  * blocks of 4, 8 or 16 warps (blockDim.x; one block per SM at 16) with ONE block barrier per
-//    iteration: the per-iteration code path is longer than the 32 KB instruction cache, and warps that
-//    drift apart evict each other's lines (measured: +60 % at n = 50 with the barrier);
+//  * the per-iteration code path is kept inside the 32 KB instruction cache (rolled loops, a rolled
+//    Philox, helpers out of line): with ~20 warps per SM each at its own place in the iteration, a longer
+//    path makes the warps evict each other's lines (ncu: stall_no_instruction 6.6 per issue on the first
+//    version; a block barrier per iteration cured that too, but made every warp wait for the slowest);
+//  * blocks of 4 or 8 warps (blockDim.x), 128 registers;
 //  * no branch on the move type: translate / rotate / swap are computed side by side and selected,
 //    so the chains of a warp do not serialise;
 //  * the two Philox blocks of an iteration are computed by different lanes of the group at once.
-template <int G>
-__global__ void __launch_bounds__(512, 1) mh_delta_kernel(const mhLaunch L)
+// EXACT = false: MH_EVAL_DELTA (delta_eval: running sums, statistically equivalent to full evaluation);
+// EXACT = true:  MH_EVAL_MEMO  (exact_eval: every total bit-identical to the full evaluation's).
+template <int G, bool EXACT>
+__global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
 {
     using WS = WarpState<G>;
     using DS = DeltaState<G>;
@@ -354,7 +336,7 @@ __global__ void __launch_bounds__(512, 1) mh_delta_kernel(const mhLaunch L)
 
     RunSums sums;
     int sel = 0;
-    float cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);   // memo and running sums of the current layout
+    float cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);   // memos (and running sums) of the current layout; = Kernel.cu:778
     float best = L.fresh ? cur : L.d_best_total[chain];
     if (L.fresh && L.result_mode == 1) {
         for (int cc = 0; cc < CPW; cc++)
@@ -377,15 +359,14 @@ __global__ void __launch_bounds__(512, 1) mh_delta_kernel(const mhLaunch L)
             beta = L.schedule == MH_SCHED_GEOMETRIC ? L.beta_start * exp2f(tt * L.beta_log2_ratio)
                                                     : L.beta_start + (L.beta_end - L.beta_start) * tt;
         }
-        if (warps > 4 && (k % L.sync_interval) == 0) __syncthreads();   // keep the block's warps in the same stretch of code
-        if (k > 0 && (it % (uint64_t)kRefresh) == 0)             // bound the drift of the running sums
+        if (!EXACT && k > 0 && (it % (uint64_t)kRefresh) == 0)   // bound the drift of the running sums
             cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);
 
         // -- random numbers: block 0 (the move) and block 1 (the acceptance uniform) of this iteration --
         Philox4 w;
         float u;
         if (G >= 2) {
-            const Philox4 mine = draw_block(L.seed, gchain, it, (uint32_t)(g & 1));
+            const Philox4 mine = draw_block<2>(L.seed, gchain, it, (uint32_t)(g & 1));
             const int l0 = LM::first_lane(c), l1 = l0 + LM::xor_step;   // the group's lanes with g = 0 and g = 1
             w.x = __shfl_sync(FULL, mine.x, l0);
             w.y = __shfl_sync(FULL, mine.y, l0);
@@ -393,8 +374,8 @@ __global__ void __launch_bounds__(512, 1) mh_delta_kernel(const mhLaunch L)
             w.w = __shfl_sync(FULL, mine.w, l0);
             u = uniform01(__shfl_sync(FULL, mine.x, l1));
         } else {
-            w = draw_block(L.seed, gchain, it, 0);
-            u = uniform01(draw_block(L.seed, gchain, it, 1).x);
+            w = draw_block<2>(L.seed, gchain, it, 0);
+            u = uniform01(draw_block<2>(L.seed, gchain, it, 1).x);
         }
 
         // -- propose (Kernel.cu:576-704), the three moves side by side ----------------------------------
@@ -405,7 +386,7 @@ __global__ void __launch_bounds__(512, 1) mh_delta_kernel(const mhLaunch L)
             a = random_int(uniform01(w.y), n - 1);
             if (p == 2) b = random_int(uniform01(w.z), n - 1);
             while (P.obj_frozen[a] || (b >= 0 && P.obj_frozen[b])) {            // Kernel.cu:601, 637, 662, 666
-                const Philox4 rw = draw_block(L.seed, gchain, it, redraw++);
+                const Philox4 rw = draw_block<2>(L.seed, gchain, it, redraw++);
                 if (P.obj_frozen[a]) a = random_int(uniform01(rw.x), n - 1);
                 if (b >= 0 && P.obj_frozen[b]) b = random_int(uniform01(rw.y), n - 1);
             }
@@ -438,19 +419,24 @@ __global__ void __launch_bounds__(512, 1) mh_delta_kernel(const mhLaunch L)
         }
         __syncwarp();
 
-        // -- evaluate: only what the moved objects touch --------------------------------------------------
+        // -- evaluate: only what the moved objects touch (EXACT: the additive terms from scratch) ---------
         RunSums star_sums;
         RelStash stash;
-        const float star = delta_eval<G>(P, S, D, c, g, sel, a_e, b_eff, oa, ob, na, nb, sums, star_sums, stash);
+        ExactStash xstash;
+        float star;
+        if (EXACT) star = exact_eval<G>(P, S, D, c, g, sel, a_e, b_eff, na, nb, xstash);
+        else star = delta_eval<G>(P, S, D, c, g, sel, a_e, b_eff, oa, ob, na, nb, sums, star_sums, stash);
 
         // -- accept (Kernel.cu:706-713) -------------------------------------------------------------------
         const bool acc = accept_move_fast(u, beta, star, cur);
         __syncwarp();
         if (acc) {
             cur = star;
-            sums = star_sums;
             sel ^= 1;
-            delta_commit<G>(P, S, D, c, g, a_e, b_eff, stash);
+            if (!EXACT) {
+                sums = star_sums;
+                delta_commit<G>(P, S, D, c, g, a_e, b_eff, stash);
+            }
             if (g == 0 && b >= 0 && live) {                      // z, rotX, rotZ travel with the swap
                 uint16_t *pm = L.d_perm + (size_t)chain * n;
                 const uint16_t pa = pm[a];
@@ -462,6 +448,7 @@ __global__ void __launch_bounds__(512, 1) mh_delta_kernel(const mhLaunch L)
             if (b >= 0) S.P4[WS::at(b, c)] = ob;
         }
         __syncwarp();
+        if (EXACT && !acc) exact_reject<G>(P, S, D, c, g, a_e, b_eff, xstash);
         if (L.result_mode == 1) {
             const bool improved = acc && cur > best;
             if (improved) best = cur;
@@ -601,38 +588,37 @@ __global__ void mh_bestkey_kernel(const float *__restrict__ best_total, const in
     *key = (long long)(k ^ 0x8000000000000000ull);
 }
 
-template <int G, int MODE> static int launch_chains_gm(const mhLaunch &L)
+template <int G> static int launch_scan_g(const mhLaunch &L)
 {
     using WS = WarpState<G>;
     const int chains_per_block = WARPS_PER_BLOCK * WS::CPW;
     const int blocks = (L.n_chains + chains_per_block - 1) / chains_per_block;
-    const int per_warp = WS::words(L.n, L.C) + (MODE == 2 ? DeltaState<G>::words(L.n, L.R, false) : 0);
-    const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)WARPS_PER_BLOCK * per_warp);
-    cudaError_t e = cudaFuncSetAttribute(mh_chain_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)WARPS_PER_BLOCK * WS::words(L.n, L.C));
+    cudaError_t e = cudaFuncSetAttribute(mh_chain_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    mh_chain_kernel<G, MODE><<<blocks, THREADS, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
+    mh_chain_kernel<G><<<blocks, THREADS, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
     return (int)cudaGetLastError();
 }
 
-template <int G> static int launch_delta_g(const mhLaunch &L)
+template <int G, bool EXACT> static int launch_delta_g(const mhLaunch &L)
 {
     using WS = WarpState<G>;
-    const int warps = L.warps_per_block == 16 || L.warps_per_block == 8 ? L.warps_per_block : 4;
+    const int warps = L.warps_per_block == 8 ? 8 : 4;
     const int chains_per_block = warps * WS::CPW;
     const int blocks = (L.n_chains + chains_per_block - 1) / chains_per_block;
     const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)warps * (WS::words(L.n, L.C) + DeltaState<G>::words(L.n, L.R, true)));
-    cudaError_t e = cudaFuncSetAttribute(mh_delta_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mh_delta_kernel<G, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    mh_delta_kernel<G><<<blocks, warps * 32, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
+    mh_delta_kernel<G, EXACT><<<blocks, warps * 32, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
     return (int)cudaGetLastError();
 }
 
 template <int G> static int launch_chains_g(const mhLaunch &L)
 {
     switch (L.eval_mode) {
-    case 1: return launch_delta_g<G>(L);
-    case 2: return launch_chains_gm<G, 2>(L);
-    default: return launch_chains_gm<G, 0>(L);
+    case 1: return launch_delta_g<G, false>(L);
+    case 2: return launch_delta_g<G, true>(L);
+    default: return launch_scan_g<G>(L);
     }
 }
 
@@ -659,7 +645,7 @@ extern "C" {
 int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int eval_mode, int warps)
 {
     int w = 0;
-    const bool memo = eval_mode == 1 || eval_mode == 2, pr = eval_mode == 1;
+    const bool memo = eval_mode == 1 || eval_mode == 2, pr = memo;
     switch (lanes) {
     case 1: w = mh::WarpState<1>::words(n, C) + (memo ? mh::DeltaState<1>::words(n, R, pr) : 0); break;
     case 2: w = mh::WarpState<2>::words(n, C) + (memo ? mh::DeltaState<2>::words(n, R, pr) : 0); break;
@@ -670,7 +656,7 @@ int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int e
     default: return -1;
     }
     if (memo && (n + lanes - 1) / lanes > 32) return -1; /* the per-lane row flags are one 32-bit word */
-    if (!pr || (warps != 8 && warps != 16)) warps = mh::WARPS_PER_BLOCK;
+    if (!memo || warps != 8) warps = mh::WARPS_PER_BLOCK;
     return 4 * (smem_words + warps * w);
 }
 

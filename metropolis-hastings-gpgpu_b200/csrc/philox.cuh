@@ -22,10 +22,13 @@ struct Philox4 {
     uint32_t x, y, z, w;
 };
 
+// UNROLL = 10: straight-line code (the full-scan kernels, whose n^2 loop dwarfs it); UNROLL = 2: a short
+// loop for the delta kernel, whose per-iteration code path must stay inside the 32 KB instruction cache.
+template <int UNROLL>
 __device__ __noinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
 {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
+#pragma unroll UNROLL
     for (int r = 0; r < 10; r++) {
         const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
         const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
@@ -39,9 +42,10 @@ __device__ __noinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     return Philox4{c0, c1, c2, c3};
 }
 
+template <int UNROLL = 10>
 __device__ __forceinline__ Philox4 draw_block(uint64_t seed, uint64_t chain, uint64_t it, uint32_t block)
 {
-    return philox4x32_10((uint32_t)it, block + ((uint32_t)(it >> 32) << 16), (uint32_t)chain, (uint32_t)(chain >> 32),
+    return philox4x32_10<UNROLL>((uint32_t)it, block + ((uint32_t)(it >> 32) << 16), (uint32_t)chain, (uint32_t)(chain >> 32),
                          (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
