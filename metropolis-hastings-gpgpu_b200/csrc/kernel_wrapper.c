@@ -29,7 +29,7 @@
 #endif
 
 #define MH_TLS __thread
-#define MH_MEMO_MIN_OBJS 64 /* nObjs from which MH_EVAL_FULL runs as the exact symmetry memo */
+#define MH_MEMO_MIN_OBJS 32 /* nObjs from which MH_EVAL_FULL runs in its bit-identical memo form (measured: -7 % at 24, +17 % at 32, +27 % at 50, 1.9x at 100, 2.7x at 200) */
 #define MH_MAX_BLOCKS_PER_SM 5 /* 128-thread blocks at the chain kernel's register cap (MH_MIN_BLOCKS in mh_kernels.cu) */
 
 static MH_TLS char g_err[512];
@@ -370,14 +370,21 @@ static int choose_delta_shape(int n, int C, int R, int smem_words, int n_chains,
         if (bytes >= 0 && bytes <= max_block) break;
         if (requested > 0) { snprintf(g_err, sizeof g_err, "lanes_per_chain=%d does not fit in shared memory (delta evaluation)", G); return -1; }
     }
-    int warps = 8;
+    /* warps per block: whichever of 8 and 4 keeps more warps resident (shared memory; 16 warps per SM is the
+     * register limit at 128 registers), 8 on a tie (the problem blob is staged once per block), and never a
+     * grid smaller than the SM count when 4 would cover it */
+    int warps = 4, best_res = -1;
     const char *wenv = getenv("MH_DELTA_WARPS");
-    if (wenv) warps = atoi(wenv) >= 8 ? 8 : 4;
     const double total_warps = ceil((double)n_chains * G / 32.0);
-    while (warps > 4) {
-        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, eval_mode, warps);
-        if (bytes >= 0 && bytes <= max_block && (wenv || total_warps / warps >= (double)sms)) break;
-        warps /= 2;
+    for (int w = 8; w >= 4; w -= 4) {
+        const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, eval_mode, w);
+        if (bytes < 0 || bytes > max_block) continue;
+        if (wenv && atoi(wenv) == w) { warps = w; break; }
+        int blocks = max_sm / (bytes + 1024);
+        if (blocks * w > 16) blocks = 16 / w;
+        int res = blocks * w;
+        if (w == 8 && total_warps / w < (double)sms) res = 0;
+        if (res > best_res) { best_res = res; warps = w; }
     }
     *lanes_out = G;
     *warps_out = warps;
@@ -492,7 +499,6 @@ MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationship
     c->eval_internal = c->opt.eval_mode == MH_EVAL_FULL_SCAN ? 0 : c->opt.eval_mode;
     c->lanes = -1;
     if (c->opt.eval_mode == MH_EVAL_FULL && c->n >= MH_MEMO_MIN_OBJS && !getenv("MH_FULL_SCAN")) {
-        /* bit-identical and faster from ~64 objects up (measured: +9% at 64, +33% at 100, +86% at 200) */
         if (choose_delta_shape(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, MH_EVAL_MEMO, &c->lanes, &c->delta_warps) == 0)
             c->eval_internal = MH_EVAL_MEMO;
         else

@@ -154,6 +154,33 @@ __device__ __forceinline__ float overlap(float4 a, float4 b)
     return pos(w) * pos(h);
 }
 
+// acc + overlap(a, b) as ONE fused multiply-add.  Every clearance sum (eval_terms' loops and the row
+// memo of exact_eval, mh_delta.cuh) goes through this, so that the rounding of a row sum does not
+// depend on where the compiler chose to contract a multiply and an add.
+__device__ __forceinline__ float overlap_add(float4 a, float4 b, float acc)
+{
+    const float w = fminf(a.z, b.z) - fmaxf(a.x, b.x);
+    const float h = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+    return fmaf(pos(w), pos(h), acc);
+}
+
+// Sum over all clearance rectangles (CBc[k * CPW], k ascending) of their overlap with box a: one row of
+// ClearanceCosts (Kernel.cu:404-434).
+template <int CPW> __device__ __forceinline__ float clearance_row(const float4 a, const float4 *CBc, const int C)
+{
+    float acc = 0.f;
+    int k = 0;
+#pragma unroll 2
+    for (; k + 2 <= C; k += 2) {
+        const float4 b0 = CBc[(k + 0) * CPW], b1 = CBc[(k + 1) * CPW];
+        acc = overlap_add(a, b0, acc);
+        acc = overlap_add(a, b1, acc);
+    }
+    for (; k < C; k++)
+        acc = overlap_add(a, CBc[k * CPW], acc);
+    return acc;
+}
+
 // Area of box b outside the room: the four complement rectangles of Kernel.cu:343-364 with
 // +-DBL_MAX narrowed to +-inf by fmaxf/fminf (Kernel.cu:325-328), i.e. no clamp on that side.
 __device__ __forceinline__ float outside_room(float4 b, const mhProblemHeader *h)
@@ -279,7 +306,7 @@ __device__ __forceinline__ void rel_pen(const SmemProblem &P, const float4 *Pc, 
 
 // All terms of one layout.  Every lane of the warp must call this (it synchronises the warp);
 // on return every lane of a group holds the group's totals.
-template <int G, bool WITH_OFFLIMITS, bool STR = false, bool SKIP_SYM = false, bool SKIP_REL = false>
+template <int G, bool WITH_OFFLIMITS, bool STR = false, bool SKIP_SYM = false, bool SKIP_REL = false, bool SKIP_CLR = false>
 __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState<G> &S, const int c, const int g, RawTerms &t)
 {
     using WS = WarpState<G>;
@@ -336,25 +363,25 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
                     const float4 q0 = Pc[j * CPW], q1 = Pc[(j + 1) * CPW], b0 = CBc[k * CPW];
                     k1 = fminf(k1, sym_key(r1, q0, pi_f));
                     k2 = fminf(k2, sym_key(r2, q0, pi_f));
-                    acc1 += overlap(a1, b0);
+                    acc1 = overlap_add(a1, b0, acc1);
                     k1 = fminf(k1, sym_key(r1, q1, pi_f));
                     k2 = fminf(k2, sym_key(r2, q1, pi_f));
-                    acc2 += overlap(a2, b0);
+                    acc2 = overlap_add(a2, b0, acc2);
                 }
             }
 #endif
 #pragma unroll 2
             for (; k + 2 <= C; k += 2) {
                 const float4 b0 = CBc[(k + 0) * CPW], b1 = CBc[(k + 1) * CPW];
-                acc1 += overlap(a1, b0);
-                acc2 += overlap(a2, b0);
-                acc1 += overlap(a1, b1);
-                acc2 += overlap(a2, b1);
+                acc1 = overlap_add(a1, b0, acc1);
+                acc2 = overlap_add(a2, b0, acc2);
+                acc1 = overlap_add(a1, b1, acc1);
+                acc2 = overlap_add(a2, b1, acc2);
             }
             for (; k < C; k++) {
                 const float4 b0 = CBc[k * CPW];
-                acc1 += overlap(a1, b0);
-                acc2 += overlap(a2, b0);
+                acc1 = overlap_add(a1, b0, acc1);
+                acc2 = overlap_add(a2, b0, acc2);
             }
             clr += acc1;                                        // row order i, i+G as in the one-row form
             clr += acc2;
@@ -395,19 +422,7 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
         // own off-limit rectangle: outside the room, against every clearance (Kernel.cu:404-434)
         const float4 a = box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y);
         surf += outside_room(a, h);
-        {
-            float acc0 = 0.f;
-            int k = 0;
-#pragma unroll 2
-            for (; k + 2 <= C; k += 2) {
-                const float4 b0 = CBc[(k + 0) * CPW], b1 = CBc[(k + 1) * CPW];
-                acc0 += overlap(a, b0);
-                acc0 += overlap(a, b1);
-            }
-            for (; k < C; k++)
-                acc0 += overlap(a, CBc[k * CPW]);
-            clr += acc0;
-        }
+        if (!SKIP_CLR) clr += clearance_row<CPW>(a, CBc, C);
         // symmetry: best match of the reflection of object i over all columns (see sym_key)
         if (!SKIP_SYM) {
             const RowRef rr = sym_row(h, pi);
@@ -443,7 +458,7 @@ __device__ __forceinline__ void eval_terms(const SmemProblem &P, const WarpState
     t.vby = group_sum<G, STR>(vby);
     t.focal = group_sum<G, STR>(focal);
     t.sym = group_sum<G, STR>(sym);
-    t.clr = group_sum<G, STR>(clr);
+    t.clr = SKIP_CLR ? 0.f : group_sum<G, STR>(clr);
     t.surf = group_sum<G, STR>(surf);
     t.off = WITH_OFFLIMITS ? group_sum<G, STR>(off) : 0.f;
 }

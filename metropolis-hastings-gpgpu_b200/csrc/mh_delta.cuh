@@ -30,21 +30,38 @@ namespace mh {
 constexpr int kDuClr = 1, kDuRow = 1, kDuScan = 1, kDuSum = 1;
 constexpr int kRefresh = 128; // iterations between full rebuilds of the memo and the running sums
 
+// Which memos a chain keeps (template parameter MODE of mh_delta_kernel):
+//   kModeDelta   MH_EVAL_DELTA: KM + PR, running sums of the additive terms;
+//   kModeExact   MH_EVAL_MEMO : KM + PR + SV, clearance rows from scratch;
+//   kModeExactCR MH_EVAL_MEMO : KM + PR + SV + CR (clearance row sums): pays when a warp holds ONE chain
+//                (rooms of ~100 objects and more); with several chains per warp some chain nearly always
+//                needs most of its rows re-added and the others wait for it.
+constexpr int kModeDelta = 0, kModeExact = 1, kModeExactCR = 2;
+
 template <int G> struct DeltaState {
     static constexpr int CPW = 32 / G;
     float2 *KM; // [2][n][CPW] {row minimum of key, a column attaining it (int bits; -1 = none below 5)}
     float2 *PR; // [R][CPW]    {distance penalty, angle penalty} of every relationship
+    float *SV;  // [n + C][CPW] exact modes: area outside the room of object i's rectangle, then of clearance k's
+    float *CR;  // [2][n][CPW] kModeExactCR: clearance row sums (object i's rectangle against every clearance)
     int n;
-    // with_pr = false: only the symmetry memo (MH_EVAL_MEMO)
-    __host__ __device__ static int words(int n, int R, bool with_pr = true) { return CPW * (4 * n + (with_pr ? 2 * R : 0)); }
-    __device__ __forceinline__ void bind(float *base, int n_, int /*R*/)
+    __host__ __device__ static int words(int n, int C, int R, int mode)
+    {
+        const int w = CPW * (4 * n + 2 * R + (mode != kModeDelta ? n + C : 0) + (mode == kModeExactCR ? 2 * n : 0));
+        return (w + 3) & ~3;                                    // the next warp's float4 state must stay 16-byte aligned
+    }
+    __device__ __forceinline__ void bind(float *base, int n_, int C, int R)
     {
         n = n_;
         KM = reinterpret_cast<float2 *>(base);
         PR = KM + 2 * n * CPW;
+        SV = reinterpret_cast<float *>(PR + R * CPW);
+        CR = SV + (n + C) * CPW;
     }
     __device__ __forceinline__ float2 &km(int sel, int i, int c) const { return KM[(sel * n + i) * CPW + c]; }
     __device__ __forceinline__ float2 &pr(int r, int c) const { return PR[r * CPW + c]; }
+    __device__ __forceinline__ float &sv(int i, int c) const { return SV[i * CPW + c]; }
+    __device__ __forceinline__ float &cr(int sel, int i, int c) const { return CR[(sel * n + i) * CPW + c]; }
 };
 
 // Committed running sums of the additive terms (positive magnitudes, as in RawTerms).
@@ -226,7 +243,7 @@ __device__ __forceinline__ float sym_rescan_sum(const SmemProblem &P, const Warp
 }
 
 // Rebuild the memo and the running sums of the CURRENT layout from scratch; returns its total.
-template <int G>
+template <int G, int MODE>
 __device__ __forceinline__ float delta_rebuild(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, int c, int g, int sel,
                                                RunSums &cur)
 {
@@ -243,6 +260,15 @@ __device__ __forceinline__ float delta_rebuild(const SmemProblem &P, const WarpS
         float pd, pa;
         rel_pen<CPW>(P, Pc, r, pd, pa);
         D.pr(r, c) = make_float2(pd, pa);
+    }
+    if (MODE != kModeDelta) {                                   // surface values; clearance row sums (S.CB is fresh)
+        for (int i = g; i < h->n; i += G) {
+            const float4 pi = Pc[i * CPW];
+            const float4 bi = box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y);
+            D.sv(i, c) = outside_room(bi, h);
+            if (i < h->C) D.sv(h->n + i, c) = outside_room(box_at(P.clr_box[i], P.clr_v0x[i], pi.x, pi.y), h);   // Q7
+            if (MODE == kModeExactCR) D.cr(sel, i, c) = clearance_row<CPW>(bi, S.CB + c, h->C);
+        }
     }
     __syncwarp();
     return combine(h, t).total;
@@ -457,35 +483,110 @@ __device__ __forceinline__ void delta_commit(const SmemProblem &P, const WarpSta
 
 // ---------------------------------------------------------------------------------------------------
 // MH_EVAL_MEMO: full evaluation, bit for bit, at a fraction of the work.  Every term of the proposal is
-// what eval_terms computes for it -- same values, added in the same order:
+// what eval_terms computes for it -- the same values, added in the same order:
 //   symmetry       the exact memo above (row minima; min is exact);
 //   relationships  only those that name a moved object are recomputed (into the PR memo); every lane
 //                  then adds ITS relationships r = g, g+G, ... from the memo, as eval_terms does;
-//   the rest       (clearance, surface, visual balance, focal) from scratch by eval_terms itself.
+//   surface        per-rectangle values in the SV memo (only the moved objects' change), re-added in
+//                  eval_terms' order: clearances k = g, g+G, ..., then objects i = g, g+G, ...;
+//   visual balance, focal   re-added from the state itself (two FMAs and an add per object);
+//   clearance      every row (object i's rectangle against all clearances, in clearance order) from
+//                  scratch -- or, kModeExactCR, from a memo of the row sums in which only the rows that
+//                  can have changed are re-added.
 // Nothing is a running sum, so nothing drifts and there is no periodic rebuild.
-struct ExactStash {
-    int r0, r1;      // relationships this lane overwrote in the PR memo ...
-    float2 o0, o1;   // ... and their penalties in the current layout (restored on rejection)
-    int overflow;    // some lane of the group overwrote more than two: rejection recomputes
+template <int G> struct ExactStash {
+    static constexpr int JOBS = (4 + G - 1) / G;   // surface jobs per lane (4 in all: objects a, b, clearances a, b)
+    int r0, r1;           // relationships this lane overwrote in the PR memo ...
+    float2 o0, o1;        // ... and their penalties in the current layout (restored on rejection)
+    int overflow;         // some lane of the group overwrote more than two: rejection recomputes
+    float sv_old[JOBS];   // the SV entries this lane overwrote
 };
 
-template <int G>
+// SV slot of surface job 0..3 (object a, object b, clearance a, clearance b; quirk Q7: clearance k sits at
+// object k's position), or -1 if there is no such rectangle.
+__device__ __forceinline__ int sv_slot(const int job, const int a, const int b, const int n, const int C)
+{
+    const int m = (job & 1) ? b : a;
+    if (m < 0) return -1;
+    if (job >= 2) return m < C ? n + m : -1;
+    return m;
+}
+
+template <int G, int MODE>
 __device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, const int c, const int g,
-                                            const int sel, const int a, const int b, const float4 na, const float4 nb, ExactStash &stash)
+                                            const int sel, const int a, const int b, const float4 na, const float4 nb, ExactStash<G> &stash)
 {
     using WS = WarpState<G>;
     constexpr int CPW = WS::CPW;
     constexpr unsigned FULL = 0xffffffffu;
     const mhProblemHeader *h = P.h;
-    const int n = h->n, R = h->R;
-    const float4 *Pc = S.P4 + c;
+    const int n = h->n, C = h->C, R = h->R;
+    const float4 *Pc = S.P4 + c, *CBc = S.CB + c;
     const bool mvb = b >= 0;
     const bool any_b = __any_sync(FULL, mvb);
     const float pi_f = 0.5f * h->two_pi;
-
     RawTerms t;
-    eval_terms<G, false, kDeltaStr, true, true>(P, S, c, g, t);   // every term but symmetry and relationships
 
+    // ---- clearance, step 1 (S.CB still holds the CURRENT layout's rectangles): which rows must be
+    //      re-added?  The moved objects' own rows, and every row whose overlap with a clearance sourced at
+    //      a moved object is non-zero before or after the move.  All other rows keep their sum bit for
+    //      bit: their terms are unchanged except for zeros that stay zeros, and x + 0 = x. -----------------
+    unsigned cflags = 0;
+    if (MODE == kModeExactCR) {
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int ca0 = P.clr_adj_off[a], na_c = P.clr_adj_off[a + 1] - ca0;
+        const int cb0 = mvb ? P.clr_adj_off[b] : 0, nb_c = mvb ? P.clr_adj_off[b + 1] - cb0 : 0;
+        const int tot = na_c + nb_c;
+        const int tmax = __reduce_max_sync(FULL, tot);
+        for (int t0 = 0; t0 < tmax; t0++) {
+            float4 mo = zero4, mn = zero4;                      // the moved clearance before / after
+            if (t0 < tot) {
+                const bool fa = t0 < na_c;
+                const int k = P.clr_adj[fa ? ca0 + t0 : cb0 + t0 - na_c];
+                const float4 pm = fa ? na : nb;
+                mo = CBc[k * CPW];
+                mn = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
+            }
+            int p = 0;
+#pragma unroll kDuRow
+            for (int i = g; i < n; i += G, p++) {
+                const float4 pi = Pc[i * CPW];
+                const float4 bi = box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y);
+                if (overlap(bi, mo) != 0.f || overlap(bi, mn) != 0.f) cflags |= 1u << p;
+            }
+        }
+        if (a % G == g) cflags |= 1u << (a / G);
+        if (mvb && b % G == g) cflags |= 1u << (b / G);
+        __syncwarp();
+    }
+
+    // ---- the clearance rectangles sourced at a moved object move with it (S.CB := the proposal's) ---------
+    for (int which = 0; which < 2; which++) {
+        const int m = which ? b : a;
+        if (m < 0) continue;
+        const float4 pm = which ? nb : na;
+        for (int tt = P.clr_adj_off[m] + g; tt < P.clr_adj_off[m + 1]; tt += G) {
+            const int k = P.clr_adj[tt];
+            S.CB[WS::at(k, c)] = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
+        }
+    }
+
+    // ---- surface values of the moved rectangles, one job per lane -------------------------------------------
+#pragma unroll
+    for (int q = 0; q < ExactStash<G>::JOBS; q++) {
+        const int job = g + q * G;
+        const int slot = job < 4 ? sv_slot(job, a, b, n, C) : -1;
+        if (slot >= 0) {
+            const int m = (job & 1) ? b : a;
+            const float4 pm = (job & 1) ? nb : na;
+            const float4 kb = job >= 2 ? P.clr_box[m] : P.obj_box[m];
+            const float v0 = job >= 2 ? P.clr_v0x[m] : P.obj_v0x[m];
+            stash.sv_old[q] = D.sv(slot, c);
+            D.sv(slot, c) = outside_room(box_at(kb, v0, pm.x, pm.y), h);
+        }
+    }
+
+    // ---- relationships that name a moved object, dealt round-robin to the lanes (as in delta_eval) --------
     stash.r0 = stash.r1 = -1;
     stash.overflow = 0;
     {
@@ -515,9 +616,49 @@ __device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpStat
         }
         if (tmax > 2 * G) stash.overflow = -group_min_int<G, kDeltaStr>(-stash.overflow);
     }
-    __syncwarp();
+    __syncwarp();                                               // S.CB, SV and PR are read by other lanes below
+
+    // ---- clearance ---------------------------------------------------------------------------------------------
+    if (MODE == kModeExactCR) {
+        // re-add the flagged rows (each lane its own, the warp pays for the lane with most), copy the others
+        unsigned todo = cflags;
+        while (__any_sync(FULL, todo != 0)) {
+            const int p = todo ? __ffs(todo) - 1 : 0;
+            const int i = todo ? g + p * G : a;                  // idle lanes shadow row a and drop the result
+            const float4 pi = Pc[i * CPW];
+            const float acc = clearance_row<CPW>(box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y), CBc, C);
+            if (todo) D.cr(1 - sel, i, c) = acc;
+            todo &= todo - 1;
+        }
+    }
+    // ---- one pass over the lane's rows, every sum in eval_terms' order -------------------------------------
     {
-        float pw = 0.f, pa = 0.f;
+        float surf = 0.f, clr = 0.f, vbx = 0.f, vby = 0.f, focal = 0.f, pw = 0.f, pa = 0.f;
+#pragma unroll kDuSum
+        for (int k = g; k < C; k += G)
+            surf += D.sv(n + k, c);
+        int p = 0;
+#pragma unroll kDuRow
+        for (int i = g; i < n; i += G, p++) {
+            const float4 pi = Pc[i * CPW];
+            const float area = P.obj_area[i];
+            vbx = fmaf(area, pi.x, vbx);
+            vby = fmaf(area, pi.y, vby);
+            focal += pi.w;
+            surf += D.sv(i, c);
+            float acc;
+            if (MODE == kModeExactCR) {
+                if ((cflags >> p) & 1u) {
+                    acc = D.cr(1 - sel, i, c);
+                } else {
+                    acc = D.cr(sel, i, c);
+                    D.cr(1 - sel, i, c) = acc;
+                }
+            } else {
+                acc = clearance_row<CPW>(box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y), CBc, C);
+            }
+            clr += acc;
+        }
 #pragma unroll kDuSum
         for (int r = g; r < R; r += G) {
             const float2 v = D.pr(r, c);
@@ -526,8 +667,15 @@ __device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpStat
         }
         t.pw = group_sum<G, kDeltaStr>(pw);
         t.pa = group_sum<G, kDeltaStr>(pa);
+        t.vbx = group_sum<G, kDeltaStr>(vbx);
+        t.vby = group_sum<G, kDeltaStr>(vby);
+        t.focal = group_sum<G, kDeltaStr>(focal);
+        t.clr = group_sum<G, kDeltaStr>(clr);
+        t.surf = group_sum<G, kDeltaStr>(surf);
+        t.off = 0.f;
     }
 
+    // ---- symmetry ------------------------------------------------------------------------------------------------
     unsigned flags = 0;
     {
         const float4 nbx = mvb ? nb : na;
@@ -540,13 +688,30 @@ __device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpStat
     return combine(h, t).total;
 }
 
-// The proposal was rejected (S.P4 is restored): put the relationship memo back.
+// The proposal was rejected (S.P4 is restored): put the clearance rectangles, the surface values and the
+// relationship memo back.
 template <int G>
 __device__ __forceinline__ void exact_reject(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, const int c, const int g,
-                                             const int a, const int b, const ExactStash &stash)
+                                             const int a, const int b, const ExactStash<G> &stash)
 {
     constexpr int CPW = WarpState<G>::CPW;
+    const int n = P.h->n, C = P.h->C;
     const float4 *Pc = S.P4 + c;
+    for (int which = 0; which < 2; which++) {
+        const int m = which ? b : a;
+        if (m < 0) continue;
+        const float4 pm = Pc[m * CPW];
+        for (int t = P.clr_adj_off[m] + g; t < P.clr_adj_off[m + 1]; t += G) {
+            const int k = P.clr_adj[t];
+            S.CB[WarpState<G>::at(k, c)] = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < ExactStash<G>::JOBS; q++) {
+        const int job = g + q * G;
+        const int slot = job < 4 ? sv_slot(job, a, b, n, C) : -1;
+        if (slot >= 0) D.sv(slot, c) = stash.sv_old[q];
+    }
     if (stash.r0 >= 0) D.pr(stash.r0, c) = stash.o0;
     if (stash.r1 >= 0) D.pr(stash.r1, c) = stash.o1;
     if (stash.overflow) {

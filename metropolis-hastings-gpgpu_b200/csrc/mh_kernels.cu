@@ -287,9 +287,10 @@ __device__ __forceinline__ bool accept_move_fast(float u, float beta, float star
 //  * no branch on the move type: translate / rotate / swap are computed side by side and selected,
 //    so the chains of a warp do not serialise;
 //  * the two Philox blocks of an iteration are computed by different lanes of the group at once.
-// EXACT = false: MH_EVAL_DELTA (delta_eval: running sums, statistically equivalent to full evaluation);
-// EXACT = true:  MH_EVAL_MEMO  (exact_eval: every total bit-identical to the full evaluation's).
-template <int G, bool EXACT>
+// MODE = kModeDelta: MH_EVAL_DELTA (delta_eval: running sums, statistically equivalent to full evaluation);
+// MODE = kModeExact / kModeExactCR: MH_EVAL_MEMO (exact_eval: every total bit-identical to the full
+// evaluation's), without / with the memo of the clearance row sums.
+template <int G, int MODE>
 __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
 {
     using WS = WarpState<G>;
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
     using LM = LaneMap<G, kDeltaStr>;
     constexpr int CPW = WS::CPW;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr bool EXACT = MODE != kModeDelta;
     extern __shared__ __align__(16) float smem[];
     const float *gprob = static_cast<const float *>(L.d_problem);
     stage_problem(smem, gprob, L.smem_words);
@@ -309,9 +311,9 @@ __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
     WS S;
     DS D;
     {
-        float *base = smem + L.smem_words + warp * (WS::words(n, C) + DS::words(n, h->R, true));
+        float *base = smem + L.smem_words + warp * (WS::words(n, C) + DS::words(n, C, h->R, MODE));
         S.bind(base, n, C);
-        D.bind(base + WS::words(n, C), n, h->R);
+        D.bind(base + WS::words(n, C), n, C, h->R);
     }
     const int chain0 = (blockIdx.x * warps + warp) * CPW;     // first chain of this warp
     const bool live = chain0 + c < L.n_chains;
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
 
     RunSums sums;
     int sel = 0;
-    float cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);   // memos (and running sums) of the current layout; = Kernel.cu:778
+    float cur = delta_rebuild<G, MODE>(P, S, D, c, g, sel, sums);   // memos (and running sums) of the current layout; = Kernel.cu:778
     float best = L.fresh ? cur : L.d_best_total[chain];
     if (L.fresh && L.result_mode == 1) {
         for (int cc = 0; cc < CPW; cc++)
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
                                                     : L.beta_start + (L.beta_end - L.beta_start) * tt;
         }
         if (!EXACT && k > 0 && (it % (uint64_t)kRefresh) == 0)   // bound the drift of the running sums
-            cur = delta_rebuild<G>(P, S, D, c, g, sel, sums);
+            cur = delta_rebuild<G, kModeDelta>(P, S, D, c, g, sel, sums);
 
         // -- random numbers: block 0 (the move) and block 1 (the acceptance uniform) of this iteration --
         Philox4 w;
@@ -422,9 +424,9 @@ __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
         // -- evaluate: only what the moved objects touch (EXACT: the additive terms from scratch) ---------
         RunSums star_sums;
         RelStash stash;
-        ExactStash xstash;
+        ExactStash<G> xstash;
         float star;
-        if (EXACT) star = exact_eval<G>(P, S, D, c, g, sel, a_e, b_eff, na, nb, xstash);
+        if (EXACT) star = exact_eval<G, MODE>(P, S, D, c, g, sel, a_e, b_eff, na, nb, xstash);
         else star = delta_eval<G>(P, S, D, c, g, sel, a_e, b_eff, oa, ob, na, nb, sums, star_sums, stash);
 
         // -- accept (Kernel.cu:706-713) -------------------------------------------------------------------
@@ -600,24 +602,24 @@ template <int G> static int launch_scan_g(const mhLaunch &L)
     return (int)cudaGetLastError();
 }
 
-template <int G, bool EXACT> static int launch_delta_g(const mhLaunch &L)
+template <int G, int MODE> static int launch_delta_g(const mhLaunch &L)
 {
     using WS = WarpState<G>;
     const int warps = L.warps_per_block == 8 ? 8 : 4;
     const int chains_per_block = warps * WS::CPW;
     const int blocks = (L.n_chains + chains_per_block - 1) / chains_per_block;
-    const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)warps * (WS::words(L.n, L.C) + DeltaState<G>::words(L.n, L.R, true)));
-    cudaError_t e = cudaFuncSetAttribute(mh_delta_kernel<G, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)warps * (WS::words(L.n, L.C) + DeltaState<G>::words(L.n, L.C, L.R, MODE)));
+    cudaError_t e = cudaFuncSetAttribute(mh_delta_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    mh_delta_kernel<G, EXACT><<<blocks, warps * 32, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
+    mh_delta_kernel<G, MODE><<<blocks, warps * 32, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
     return (int)cudaGetLastError();
 }
 
 template <int G> static int launch_chains_g(const mhLaunch &L)
 {
     switch (L.eval_mode) {
-    case 1: return launch_delta_g<G, false>(L);
-    case 2: return launch_delta_g<G, true>(L);
+    case 1: return launch_delta_g<G, kModeDelta>(L);
+    case 2: return launch_delta_g<G, (G == 32 ? kModeExactCR : kModeExact)>(L);
     default: return launch_scan_g<G>(L);
     }
 }
@@ -638,6 +640,12 @@ static int launch_score_g(const void *d_problem, int smem_words, int n, int C, i
     return (int)cudaGetLastError();
 }
 
+template <int G> static int chain_words(int n, int C, int R, int eval_mode)
+{
+    const int dm = eval_mode == 1 ? kModeDelta : (G == 32 ? kModeExactCR : kModeExact);
+    return WarpState<G>::words(n, C) + (eval_mode == 1 || eval_mode == 2 ? DeltaState<G>::words(n, C, R, dm) : 0);
+}
+
 } // namespace mh
 
 extern "C" {
@@ -645,14 +653,14 @@ extern "C" {
 int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int eval_mode, int warps)
 {
     int w = 0;
-    const bool memo = eval_mode == 1 || eval_mode == 2, pr = memo;
+    const bool memo = eval_mode == 1 || eval_mode == 2;
     switch (lanes) {
-    case 1: w = mh::WarpState<1>::words(n, C) + (memo ? mh::DeltaState<1>::words(n, R, pr) : 0); break;
-    case 2: w = mh::WarpState<2>::words(n, C) + (memo ? mh::DeltaState<2>::words(n, R, pr) : 0); break;
-    case 4: w = mh::WarpState<4>::words(n, C) + (memo ? mh::DeltaState<4>::words(n, R, pr) : 0); break;
-    case 8: w = mh::WarpState<8>::words(n, C) + (memo ? mh::DeltaState<8>::words(n, R, pr) : 0); break;
-    case 16: w = mh::WarpState<16>::words(n, C) + (memo ? mh::DeltaState<16>::words(n, R, pr) : 0); break;
-    case 32: w = mh::WarpState<32>::words(n, C) + (memo ? mh::DeltaState<32>::words(n, R, pr) : 0); break;
+    case 1: w = mh::chain_words<1>(n, C, R, eval_mode); break;
+    case 2: w = mh::chain_words<2>(n, C, R, eval_mode); break;
+    case 4: w = mh::chain_words<4>(n, C, R, eval_mode); break;
+    case 8: w = mh::chain_words<8>(n, C, R, eval_mode); break;
+    case 16: w = mh::chain_words<16>(n, C, R, eval_mode); break;
+    case 32: w = mh::chain_words<32>(n, C, R, eval_mode); break;
     default: return -1;
     }
     if (memo && (n + lanes - 1) / lanes > 32) return -1; /* the per-lane row flags are one 32-bit word */

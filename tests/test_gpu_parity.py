@@ -498,11 +498,35 @@ def test_memo_mode_is_bit_identical_to_full_scan(kernel, cid, lanes, chains, ite
 
 
 def test_default_mode_switches_to_the_memo_transparently(kernel):
-    """MH_EVAL_FULL uses the memo form from 64 objects up; callers must not be able to tell."""
-    room = S.make_room(70, 30, 40, 10.0, 8.0, 99)
-    pa, ca = kernel.wrapper_ex(room, 48, 150, seed=3, lanes_per_chain=8, eval_mode=0)
-    pb, cb = kernel.wrapper_ex(room, 48, 150, seed=3, lanes_per_chain=8, eval_mode=3)
-    assert pa.tobytes() == pb.tobytes() and ca.tobytes() == cb.tobytes()
+    """MH_EVAL_FULL uses the memo form from 32 objects up; callers must not be able to tell."""
+    for n, C, R, lanes in ((70, 30, 40, 8), (33, 16, 20, 4), (120, 60, 90, 32)):
+        room = S.make_room(n, C, R, 10.0, 8.0, 99)
+        pa, ca = kernel.wrapper_ex(room, 48, 150, seed=3, lanes_per_chain=lanes, eval_mode=0)
+        pb, cb = kernel.wrapper_ex(room, 48, 150, seed=3, lanes_per_chain=lanes, eval_mode=3)
+        assert pa.tobytes() == pb.tobytes() and ca.tobytes() == cb.tobytes(), n
+
+
+def test_memo_and_delta_on_wild_rooms_every_lane_width(kernel, oracle):
+    """The memo form against the full scan, bit for bit, and the delta form against a fresh evaluation, on
+    rooms with shared clearance sources, relationship hubs, frozen objects and odd sizes, for every lane
+    width (32 lanes = the variant that also memoises the clearance row sums)."""
+    for seed in range(10):
+        g = np.random.default_rng(7000 + seed)
+        n = int(g.integers(1, 70))
+        room = S.make_wild_room(n, int(g.integers(0, n + 1)), int(g.integers(0, 60)), 500 + seed)
+        for lanes in (1, 2, 8, 16, 32):
+            if (n + lanes - 1) // lanes > 32:
+                continue
+            kw = dict(seed=seed, lanes_per_chain=lanes, result_mode=seed % 2)
+            ps, cs = kernel.wrapper_ex(room, 20, 90, eval_mode=3, **kw)
+            pm, cm = kernel.wrapper_ex(room, 20, 90, eval_mode=2, **kw)
+            assert ps.tobytes() == pm.tobytes() and cs.tobytes() == cm.tobytes(), (seed, n, lanes)
+            with kernel.create(room, 20, seed=seed, eval_mode=1, lanes_per_chain=lanes) as ctx:
+                tr = ctx.run_traced(90)
+                _, costs = ctx.results()
+            fresh = costs["totalCosts"]
+            scale = np.abs(fresh) + sum(np.abs(costs[f]) for f in L.COST_FIELDS[1:])
+            assert np.all(np.abs(tr["cur_total"][-1] - fresh) <= 2e-5 * scale + 1e-3), (seed, n, lanes)
 
 
 def test_memo_mode_with_frozen_swaps_and_tempering(kernel):

@@ -7,8 +7,13 @@ pkg = importlib.import_module("metropolis-hastings-gpgpu_b200")
 tag = sys.argv[1]
 k = pkg.Kernel()
 for spec in sys.argv[2:]:
-    cid, chains, iters, lanes, mode = [int(v) for v in spec.split(":")]
-    room = pkg.synth.make_config(cid)
+    cid, chains, iters, lanes, mode = spec.split(":")
+    chains, iters, lanes, mode = int(chains), int(iters), int(lanes), int(mode)
+    if "x" in cid:                                              # custom room "NxCxR" on a 12 x 9 floor
+        room = pkg.synth.make_room(*[int(v) for v in cid.split("x")], 12.0, 9.0, 4242)
+    else:
+        cid = int(cid)
+        room = pkg.synth.make_config(cid)
     try:
         with k.create(room, chains, seed=1, lanes_per_chain=lanes, eval_mode=mode) as ctx:
             ctx.run(iters); ctx.synchronize(); ms0, _ = ctx.stats()
