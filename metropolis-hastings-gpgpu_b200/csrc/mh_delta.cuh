@@ -33,9 +33,15 @@ constexpr int kRefresh = 128; // iterations between full rebuilds of the memo an
 // Which memos a chain keeps (template parameter MODE of mh_delta_kernel):
 //   kModeDelta   MH_EVAL_DELTA: KM + PR, running sums of the additive terms;
 //   kModeExact   MH_EVAL_MEMO : KM + PR + SV, clearance rows from scratch;
-//   kModeExactCR MH_EVAL_MEMO : KM + PR + SV + CR (clearance row sums): pays when a warp holds ONE chain
-//                (rooms of ~100 objects and more); with several chains per warp some chain nearly always
-//                needs most of its rows re-added and the others wait for it.
+//   kModeExactCR MH_EVAL_MEMO : KM + PR + SV + CR (clearance row sums): used when a warp holds one or two
+//                chains (16 and 32 lanes per chain, rooms of ~100 objects and more: +17 % at n = 100, 1.6x
+//                at n = 200).  With more chains per warp some chain nearly always has many rows to re-add
+//                and the others wait for it (on the dense 50-object room a third of the rows overlaps a
+//                moved clearance): measured slower than re-adding every row, also when the flagged rows of
+//                all chains were dealt to the warp's 32 lanes (ballots + find-nth-set push the code out of
+//                the instruction cache), and also with an 8 x 4 grid of candidate clearances per row
+//                (exact -- zero overlaps do not change a float sum -- but the per-lane candidate lists turn
+//                the broadcast shared-memory loads of the regular loop into scattered ones: 2x slower).
 constexpr int kModeDelta = 0, kModeExact = 1, kModeExactCR = 2;
 
 template <int G> struct DeltaState {

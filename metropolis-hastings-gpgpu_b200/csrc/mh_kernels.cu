@@ -602,6 +602,9 @@ template <int G> static int launch_scan_g(const mhLaunch &L)
     return (int)cudaGetLastError();
 }
 
+// the memo form keeps clearance row sums only when a warp holds one or two chains (mh_delta.cuh)
+constexpr int exact_mode(int G) { return G >= 16 ? kModeExactCR : kModeExact; }
+
 template <int G, int MODE> static int launch_delta_g(const mhLaunch &L)
 {
     using WS = WarpState<G>;
@@ -619,7 +622,7 @@ template <int G> static int launch_chains_g(const mhLaunch &L)
 {
     switch (L.eval_mode) {
     case 1: return launch_delta_g<G, kModeDelta>(L);
-    case 2: return launch_delta_g<G, (G == 32 ? kModeExactCR : kModeExact)>(L);
+    case 2: return launch_delta_g<G, exact_mode(G)>(L);
     default: return launch_scan_g<G>(L);
     }
 }
@@ -642,7 +645,7 @@ static int launch_score_g(const void *d_problem, int smem_words, int n, int C, i
 
 template <int G> static int chain_words(int n, int C, int R, int eval_mode)
 {
-    const int dm = eval_mode == 1 ? kModeDelta : (G == 32 ? kModeExactCR : kModeExact);
+    const int dm = eval_mode == 1 ? kModeDelta : exact_mode(G);
     return WarpState<G>::words(n, C) + (eval_mode == 1 || eval_mode == 2 ? DeltaState<G>::words(n, C, R, dm) : 0);
 }
 
