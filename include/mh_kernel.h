@@ -46,12 +46,13 @@ enum {
 
 enum {
     MH_EVAL_FULL = 0, /* every proposal re-evaluates every live cost term from scratch (Kernel.cu:804); for
-                         nObjs >= 64 the library uses the bit-identical MH_EVAL_MEMO form, which is faster  */
+                         nObjs >= 32 the library uses the bit-identical MH_EVAL_MEMO form, which is faster  */
     MH_EVAL_FULL_SCAN = 3, /* MH_EVAL_FULL with the plain n^2 scan forced (verification)                    */
-    MH_EVAL_MEMO = 2, /* full evaluation whose O(n^2) symmetry term comes from an exact memo of the row
-                         minima: bit-identical totals to MH_EVAL_FULL for the same lane width            */
-    MH_EVAL_DELTA = 1 /* incremental evaluation: only what the moved objects touch is recomputed, the
-                         memo is rebuilt from scratch every 128 iterations; statistically equivalent to
+    MH_EVAL_MEMO = 2, /* full evaluation through exact memos (symmetry row minima, relationship penalties,
+                         surface values, clearance row sums): totals bit-identical to MH_EVAL_FULL_SCAN
+                         for the same lane width                                                         */
+    MH_EVAL_DELTA = 1 /* incremental evaluation: only what the moved objects touch is recomputed, running
+                         sums rebuilt from scratch every 128 iterations; statistically equivalent to
                          MH_EVAL_FULL, not bit-identical (csrc/mh_delta.cuh)                            */
 };
 
