@@ -42,6 +42,10 @@ constexpr int kRefresh = 128; // iterations between full rebuilds of the memo an
 //                the instruction cache), and also with an 8 x 4 grid of candidate clearances per row
 //                (exact -- zero overlaps do not change a float sum -- but the per-lane candidate lists turn
 //                the broadcast shared-memory loads of the regular loop into scattered ones: 2x slower).
+//                Why so many rows are flagged: the sampler MAXIMISES totalCosts (quirk Q10), with negative
+//                weights that rewards overlap, so the chains pile objects up.  (Re-adding one flagged row per
+//                pass with the whole group -- overlaps side by side, the non-zero ones then added in order
+//                through shuffles -- was 2.3x slower at n = 200 for the same reason: dozens of rows per move.)
 constexpr int kModeDelta = 0, kModeExact = 1, kModeExactCR = 2;
 
 template <int G> struct DeltaState {
