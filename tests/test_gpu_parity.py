@@ -432,6 +432,28 @@ def test_delta_distribution_matches_oracle_ks(kernel, oracle):
         assert stats.ks_2samp(ck["totalCosts"], co["totalCosts"]).pvalue > 0.01, cid
 
 
+def test_delta_distribution_config3_ks(kernel, oracle):
+    """Delta evaluation on the 50-object room (8 lanes per chain, the shape the bench reports) against the
+    oracle's full evaluation: final totalCosts of 4096 chains, disjoint seeds, two-sample KS."""
+    room = S.make_config(3)
+    _, ck = kernel.wrapper_ex(room, 4096, 260, seed=77, eval_mode=1)
+    _, co = oracle.run(room, 4096, 260, seed=7070)
+    assert stats.ks_2samp(ck["totalCosts"], co["totalCosts"]).pvalue > 0.01
+
+
+def test_memo_mode_with_annealing_and_resume(kernel):
+    """The memo form under a geometric beta schedule, split over two calls, against the plain scan."""
+    room = S.make_config(3)
+    out = []
+    for mode in (3, 2):
+        with kernel.create(room, 48, seed=5, eval_mode=mode, lanes_per_chain=8, beta_start=0.5, beta_end=12.0, schedule=1,
+                           schedule_length=240, result_mode=1) as ctx:
+            ctx.run(100)
+            ctx.run(140)
+            out.append(ctx.results())
+    assert out[0][0].tobytes() == out[1][0].tobytes() and out[0][1].tobytes() == out[1][1].tobytes()
+
+
 def test_delta_with_frozen_best_and_annealing(kernel, oracle):
     room = S.make_config(2)
     room.cfg["frozen"][[2, 9]] = 1
