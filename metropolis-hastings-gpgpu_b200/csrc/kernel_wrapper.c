@@ -336,7 +336,10 @@ static int choose_lanes(int n, int C, int R, int smem_words, int n_chains, int r
         if (per_sm > cap_warps) per_sm = cap_warps;
         const double cover = per_sm >= 18.0 ? 1.0 : per_sm / 18.0;
         const double rows = ceil((double)n / G);
-        const double cost = G * (450.0 + rows * (12.0 * n + 8.0 * C + 100.0)) / 32.0;
+        /* warp instructions of the whole job: with chains to spare this is proportional to G (the old form of
+         * the model); with fewer chains than a warp holds it is not -- one chain is one warp for every G, and
+         * the widest group, i.e. the shortest per-lane program, wins (measured: 13.7 -> 3.0 ms for 1 chain x 1000 iterations at n=16) */
+        const double cost = warps_total * (450.0 + rows * (12.0 * n + 8.0 * C + 100.0));
         const double score = cover / cost;
         if (score > best_score * 1.03) { /* near-ties go to the wider group (less shared memory) */
             best_score = score;
