@@ -57,6 +57,17 @@ __device__ __forceinline__ bool accept_move(float u, float beta, float star, flo
     return u < fminf(1.0f, (float)exp((double)beta * ((double)star - (double)cur)));
 }
 
+// u < min(1, exp(x)), x = beta (star - cur) in double (accept_move), decided from a float estimate of the
+// exponential whenever u is clear of the threshold by more than the estimate's error; the rare
+// in-between case (probability ~2e-4) takes the double-precision exponential.  Same decisions, always.
+__device__ __forceinline__ bool accept_move_fast(float u, float beta, float star, float cur)
+{
+    const float ef = __expf(beta * (star - cur));                // relative error < 4e-5 for |x| <= 100
+    if (u < fminf(1.0f, ef * 0.9999f)) return true;
+    if (u >= ef * 1.0001f) return false;
+    return accept_move(u, beta, star, cur);
+}
+
 template <int G>
 __device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc, int n, const float *pass, const uint16_t *perm,
                                                   PointRec *out, int lane)
@@ -153,8 +164,22 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
                                                     : L.beta_start + (L.beta_end - L.beta_start) * tt;
         }
 
-        // -- propose (Kernel.cu:576-704): every lane of the group derives the same move -------------
-        const Philox4 w = draw_block(L.seed, gchain, it, 0);
+        // -- propose (Kernel.cu:576-704): every lane of the group derives the same move; the two Philox
+        //    blocks of the iteration (move, acceptance uniform) are computed by different lanes at once --
+        Philox4 w;
+        float u;
+        if (G >= 2) {
+            const Philox4 mine = draw_block(L.seed, gchain, it, (uint32_t)(g & 1));
+            const int l0 = LM::first_lane(c);
+            w.x = __shfl_sync(0xffffffffu, mine.x, l0);
+            w.y = __shfl_sync(0xffffffffu, mine.y, l0);
+            w.z = __shfl_sync(0xffffffffu, mine.z, l0);
+            w.w = __shfl_sync(0xffffffffu, mine.w, l0);
+            u = uniform01(__shfl_sync(0xffffffffu, mine.x, l0 + 1));
+        } else {
+            w = draw_block(L.seed, gchain, it, 0);
+            u = uniform01(draw_block(L.seed, gchain, it, 1).x);
+        }
         const int p = random_int(uniform01(w.x), 2);
         int a = -1, b = -1;
         float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;   // proposed state of objects a, b
@@ -207,8 +232,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
         }
 
         // -- accept (Kernel.cu:706-713): u < min(1, exp(beta (star - cur))), maximises (Q10) ------
-        const float u = uniform01(draw_block(L.seed, gchain, it, 1).x);
-        const bool acc = accept_move(u, beta, star, cur);
+        const bool acc = accept_move_fast(u, beta, star, cur);
         __syncwarp();
         if (acc) {
             cur = star;
@@ -265,17 +289,6 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
             if (ch < L.n_chains) write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)ch * n, points + (size_t)ch * n, lane);
         }
     }
-}
-
-// u < min(1, exp(x)), x = beta (star - cur) in double (accept_move), decided from a float estimate of the
-// exponential whenever u is clear of the threshold by more than the estimate's error; the rare
-// in-between case (probability ~2e-4) takes the double-precision exponential.  Same decisions, always.
-__device__ __forceinline__ bool accept_move_fast(float u, float beta, float star, float cur)
-{
-    const float ef = __expf(beta * (star - cur));                // relative error < 4e-5 for |x| <= 100
-    if (u < fminf(1.0f, ef * 0.9999f)) return true;
-    if (u >= ef * 1.0001f) return false;
-    return accept_move(u, beta, star, cur);
 }
 
 // The chain of mh_chain_kernel with incremental evaluation (mh_delta.cuh).  Differences in shape:

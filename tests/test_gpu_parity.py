@@ -275,6 +275,17 @@ def test_final_cost_distribution_config3_ks(kernel, oracle):
         assert p > 0.005, (f, p)
 
 
+def test_final_cost_distribution_config4_ks(kernel, oracle):
+    """BASELINE config 4 (200 objects; the default runs the memo form with clearance row sums, 32 lanes per
+    chain): two-sample KS on the final totalCosts, default and delta evaluation against the oracle."""
+    room = S.make_config(4)
+    _, co = oracle.run(room, 1024, 100, seed=31337)
+    _, ck = kernel.wrapper_ex(room, 1024, 100, seed=4242)
+    _, cd = kernel.wrapper_ex(room, 1024, 100, seed=4343, eval_mode=1)
+    assert stats.ks_2samp(ck["totalCosts"], co["totalCosts"]).pvalue > 0.01
+    assert stats.ks_2samp(cd["totalCosts"], co["totalCosts"]).pvalue > 0.01
+
+
 def test_frozen_objects_and_passthrough(kernel):
     room = S.make_config(1)
     room.cfg["frozen"][[1, 6]] = 1
