@@ -17,7 +17,7 @@ _P = C.c_void_p
 
 EXPORTS = ("KernelWrapper", "KernelWrapperEx", "KernelFree", "KernelLastError", "KernelEvalCosts", "KernelCreate", "KernelRun",
            "KernelRunTraced", "KernelSynchronize", "KernelResults", "KernelDeviceResults", "KernelSetStream", "KernelBest",
-           "KernelStats", "KernelDestroy", "KernelDeviceInfo", "KernelBestKey", "KernelDecodeBestKey", "KernelReset", "KernelTrim", "KernelTemperingState", "KernelTemperingExchange", "KernelTopK")
+           "KernelStats", "KernelDestroy", "KernelDeviceInfo", "KernelBestKey", "KernelDecodeBestKey", "KernelReset", "KernelTrim", "KernelTemperingState", "KernelTemperingExchange", "KernelTopK", "KernelTopKDistinct")
 
 
 class KernelError(RuntimeError):
@@ -70,6 +70,7 @@ class Kernel:
             lib.KernelBestKey.argtypes = [_P, _P]
             lib.KernelReset.argtypes = [_P]
             lib.KernelTopK.argtypes = [_P, C.c_int, _P, _P]
+            lib.KernelTopKDistinct.argtypes = [_P, C.c_int, C.c_float, C.c_float, _P, _P]
             lib.KernelTemperingState.argtypes = [_P, C.POINTER(_P), C.POINTER(_P)]
             lib.KernelTemperingExchange.argtypes = [_P, _P, _P]
             lib.KernelDecodeBestKey.argtypes = [C.c_longlong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]
@@ -248,6 +249,14 @@ class Context:
         m = self.k.lib.KernelTopK(self.h, C.c_int(k), _ptr(idx), _ptr(tot))
         if m < 0:
             self.k._fail("KernelTopK")
+        return idx[:m], tot[:m]
+
+    def top_k_distinct(self, k, min_distance, rot_weight=0.0):
+        idx = np.zeros(k, np.int32)
+        tot = np.zeros(k, np.float32)
+        m = self.k.lib.KernelTopKDistinct(self.h, C.c_int(k), C.c_float(min_distance), C.c_float(rot_weight), _ptr(idx), _ptr(tot))
+        if m < 0:
+            self.k._fail("KernelTopKDistinct")
         return idx[:m], tot[:m]
 
     def stats(self):

@@ -816,6 +816,43 @@ fail:
     return rc;
 }
 
+MH_API int KernelTopKDistinct(mhContext *ctx, int k, float minDistance, float rotWeight, int *chains, float *totals)
+{
+    int prev = -1, rc = -1, found = 0;
+    float *d_mind = NULL, *fill = NULL;
+    g_err[0] = 0;
+    if (!ctx || k < 1 || !(minDistance >= 0.f) || !(rotWeight >= 0.f)) { set_err("", "bad arguments", 0); return -1; }
+    if (k > ctx->n_chains) k = ctx->n_chains;
+    CU(enter_device(ctx->device, &prev));
+    CU(ensure_scored(ctx));
+    /* d_mind = +inf: 0x7f800000 cannot be memset bytewise, so it is copied from the host once */
+    fill = (float *)malloc(sizeof(float) * (size_t)ctx->n_chains);
+    if (!fill) { set_err("", "out of host memory", 0); goto fail; }
+    for (int i = 0; i < ctx->n_chains; i++) fill[i] = INFINITY;
+    CU(mhdev_malloc((void **)&d_mind, sizeof(float) * (size_t)ctx->n_chains, ctx->stream));
+    CU(mhdev_h2d(d_mind, fill, sizeof(float) * (size_t)ctx->n_chains, ctx->stream));
+    for (found = 0; found < k; found++) {
+        struct { float total; int chain; } best;
+        CU(mhdev_launch_pick_distinct(ctx->d_costs, d_mind, ctx->n_chains, found ? minDistance : -1.0f, ctx->d_scratch, ctx->stream));
+        CU(mhdev_d2h(&best, ctx->d_scratch, sizeof best, ctx->stream));
+        CU(mhdev_stream_sync(ctx->stream));
+        ctx->launches++;
+        if (best.chain < 0) break;                              /* every remaining chain is a near-duplicate */
+        if (chains) chains[found] = best.chain;
+        if (totals) totals[found] = best.total;
+        if (found + 1 < k) {
+            CU(mhdev_launch_distance(ctx->d_points, ctx->n, ctx->n_chains, best.chain, rotWeight, (float)(2 * MH_PI), d_mind, ctx->stream));
+            ctx->launches++;
+        }
+    }
+    rc = found;
+fail:
+    if (d_mind) { mhdev_stream_sync(ctx->stream); mhdev_free(d_mind, ctx->stream); }
+    free(fill);
+    if (prev >= 0) leave_device(ctx->device, prev);
+    return rc;
+}
+
 MH_API int KernelBestKey(mhContext *ctx, void *d_key)
 {
     int prev = -1, rc = -1;

@@ -102,6 +102,11 @@ int mhdev_launch_exchange(int n_chains, uint64_t chain_offset, uint64_t chain_st
                           uint64_t gather_base, uint64_t gather_stride, uint64_t gather_local, float *d_beta, void *stream);
 /* arg-max of totalCosts over the context's chains: d_out = {float total, int32 chain}. */
 int mhdev_launch_argmax(const void *d_costs, int n_chains, void *d_out, void *stream);
+/* Distinct suggestions: d_mind[chain] = min(d_mind[chain], distance of the chain's layout to ref_chain's);
+ * then the best chain with d_mind > min_dist: d_out = {float total, int32 chain or -1}. */
+int mhdev_launch_distance(const void *d_points, int n, int n_chains, int ref_chain, float rot_weight, float two_pi, float *d_mind,
+                          void *stream);
+int mhdev_launch_pick_distinct(const void *d_costs, const float *d_mind, int n_chains, float min_dist, void *d_out, void *stream);
 /* d_key (device int64) = order-preserving (totalCosts, global chain id) key of the arg-max result. */
 int mhdev_launch_bestkey(const void *d_argmax_out, uint64_t chain_offset, uint64_t chain_stride, void *d_key, void *stream);
 /* Largest dynamic shared memory per block and SM count / clock of the current device. */

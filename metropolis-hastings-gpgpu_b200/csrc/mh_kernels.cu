@@ -589,6 +589,61 @@ __global__ void mh_argmax_kernel(const Costs8 *__restrict__ costs, int n, float 
     }
 }
 
+// Distinct suggestions (KernelTopKDistinct).  How far is every chain's layout from a reference chain's?  The
+// distance of two layouts is the largest displacement of any object, max_i max(|dx|, |dy|, rot_weight |drot|)
+// with the rotation difference wrapped into [0, PI]; mind[chain] keeps the minimum over the references seen
+// so far.  One warp per chain, lanes over objects.
+__global__ void mh_distance_kernel(const PointRec *__restrict__ points, int n, int n_chains, int ref_chain, float rot_weight, float two_pi,
+                                   float *__restrict__ mind)
+{
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (chain >= n_chains) return;
+    const PointRec *a = points + (size_t)chain * n, *b = points + (size_t)ref_chain * n;
+    float d = 0.f;
+    for (int i = lane; i < n; i += 32) {
+        const PointRec p = a[i], q = b[i];
+        float dr = fabsf(p.rotY - q.rotY);
+        dr = fminf(dr, fabsf(two_pi - dr));
+        d = fmaxf(d, fmaxf(fmaxf(fabsf(p.x - q.x), fabsf(p.y - q.y)), rot_weight * dr));
+    }
+    for (int m = 16; m > 0; m >>= 1)
+        d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, m));
+    if (lane == 0) mind[chain] = fminf(mind[chain], d);
+}
+
+// The chain with the highest totalCosts among those farther than min_dist from every reference so far
+// (ties: lower index); out = {total, index}, index -1 if none is left.
+__global__ void mh_pick_distinct_kernel(const Costs8 *__restrict__ costs, const float *__restrict__ mind, int n, float min_dist,
+                                        float *out_total, int *out_idx)
+{
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    float bv = -INFINITY;
+    int bi = -1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = costs[i].total;
+        if (mind[i] > min_dist && (bi < 0 || v > bv)) { bv = v; bi = i; }
+    }
+    for (int m = 16; m > 0; m >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, m);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+        if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) / 32;
+        bv = threadIdx.x < nw ? sv[threadIdx.x] : -INFINITY;
+        bi = threadIdx.x < nw ? si[threadIdx.x] : -1;
+        for (int m = 16; m > 0; m >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, m);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+            if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) { *out_total = bv; *out_idx = bi; }
+    }
+}
+
 // Packs the context's best chain for a MAX all-reduce: NCCL has no arg-max, so the totalCosts
 // (made order-preserving as an unsigned integer) goes in the high word and the complemented
 // global chain id in the low word (ties go to the lower id); the top bit is flipped so that a
@@ -730,6 +785,23 @@ int mhdev_launch_argmax(const void *d_costs, int n_chains, void *d_out, void *st
     mh::mh_argmax_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const mh::Costs8 *>(d_costs), n_chains,
                                                                            static_cast<float *>(d_out),
                                                                            reinterpret_cast<int *>(static_cast<float *>(d_out) + 1));
+    return (int)cudaGetLastError();
+}
+
+int mhdev_launch_distance(const void *d_points, int n, int n_chains, int ref_chain, float rot_weight, float two_pi, float *d_mind,
+                          void *stream)
+{
+    const long long threads = (long long)n_chains * 32;
+    mh::mh_distance_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const mh::PointRec *>(d_points), n, n_chains, ref_chain, rot_weight, two_pi, d_mind);
+    return (int)cudaGetLastError();
+}
+
+int mhdev_launch_pick_distinct(const void *d_costs, const float *d_mind, int n_chains, float min_dist, void *d_out, void *stream)
+{
+    mh::mh_pick_distinct_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const mh::Costs8 *>(d_costs), d_mind, n_chains, min_dist, static_cast<float *>(d_out),
+        reinterpret_cast<int *>(static_cast<float *>(d_out) + 1));
     return (int)cudaGetLastError();
 }
 

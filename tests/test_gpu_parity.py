@@ -340,6 +340,38 @@ def test_kernel_best_is_argmax(kernel):
     assert np.array_equal(idx, order[:10]) and np.array_equal(tot, c["totalCosts"][order[:10]]) and len(big) == 1000
 
 
+def test_top_k_distinct_is_the_greedy_selection(kernel):
+    """KernelTopKDistinct against a host-side greedy selection on the returned layouts: best first, a chain
+    is taken if it is farther than min_distance (largest object displacement) from every chain taken."""
+    room = S.make_config(2)
+    with kernel.create(room, 2048, seed=11) as ctx:
+        ctx.run(150)
+        pts, costs = ctx.results()
+        for min_d, rw in ((0.75, 0.0), (1.5, 0.0), (1.0, 0.5), (1e9, 0.0)):
+            idx, tot = ctx.top_k_distinct(12, min_d, rw)
+            order = np.lexsort((np.arange(2048), -costs["totalCosts"].astype(np.float64)))
+            taken = []
+            for ch in order:
+                ok = True
+                for t in taken:
+                    dr = np.abs(pts["rotY"][ch] - pts["rotY"][t])
+                    dr = np.minimum(dr, np.abs(np.float32(2 * L.PI) - dr))
+                    d = max(np.abs(pts["x"][ch] - pts["x"][t]).max(), np.abs(pts["y"][ch] - pts["y"][t]).max(), (np.float32(rw) * dr).max())
+                    if not d > min_d:
+                        ok = False
+                        break
+                if ok:
+                    taken.append(int(ch))
+                    if len(taken) == 12:
+                        break
+            assert list(idx) == taken, (min_d, rw)
+            assert np.all(tot == costs["totalCosts"][idx])
+        assert len(ctx.top_k_distinct(12, 1e9)[0]) == 1            # everything is within 1e9 of the best
+        i1, _ = ctx.top_k(5)
+        i2, _ = ctx.top_k_distinct(5, 0.0)
+        assert i2[0] == i1[0]
+
+
 def test_full_size_properties_config3(kernel, oracle):
     """BASELINE config 3 room at a reduced iteration count: properties that do not need the
     oracle to run the chains -- reported costs are the cost function of the returned layouts,
