@@ -492,6 +492,94 @@ __device__ __forceinline__ void delta_commit(const SmemProblem &P, const WarpSta
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Relationship memo of the memo form (exact_eval): PR[r] holds the penalties of every relationship in the CURRENT layout.  A
+// proposal re-evaluates only the relationships that name a moved object (CSR by object; one that names both
+// is taken from a's list only), dealt round-robin to the lanes of the group, and overwrites their entries;
+// then every lane adds ITS relationships r = g, g+G, ... from the memo -- the values and the order of
+// eval_terms' relationship loop, hence the same bits.  A rejected proposal puts the old entries back.
+// (The same memo inside the plain scan kernel, for rooms below 32 objects, was measured slower than evaluating
+// all R relationships: 1.7e9 against 2.4e9 proposals/s at n = 16 -- with 16 chains per warp the warp pays
+// for the chain with most touched relationships, and the kernel started to spill.)
+struct RelMemoStash {
+    int r0, r1;      // relationships this lane overwrote ...
+    float2 o0, o1;   // ... and their penalties in the current layout
+    int overflow;    // some lane of the group overwrote more than two: rejection recomputes
+};
+
+// PRc = the chain's memo (entry r at PRc[r * CPW]); Pc = its state, holding the proposal; a < 0: no move.
+// Every lane of the warp must call this.  Returns the two sums reduced over the group.
+template <int G, bool STR>
+__device__ __forceinline__ void rel_memo_eval(const SmemProblem &P, const float4 *Pc, float2 *PRc, const int g, const int a, const int b,
+                                              RelMemoStash &stash, float &pw_total, float &pa_total)
+{
+    constexpr int CPW = 32 / G;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int R = P.h->R;
+    const bool mva = a >= 0, mvb = b >= 0;
+    stash.r0 = stash.r1 = -1;
+    stash.overflow = 0;
+    {
+        const int ra0 = mva ? P.rel_adj_off[a] : 0, na_r = mva ? P.rel_adj_off[a + 1] - ra0 : 0;
+        const int rb0 = mvb ? P.rel_adj_off[b] : 0, nb_r = mvb ? P.rel_adj_off[b + 1] - rb0 : 0;
+        const int tot = na_r + nb_r;
+        const int tmax = __reduce_max_sync(FULL, tot);
+        int slot = 0;
+        for (int tt = g; tt < tmax; tt += G, slot++) {
+            int r = -1;
+            if (tt < na_r) {
+                r = P.rel_adj[ra0 + tt];
+            } else if (tt < tot) {
+                r = P.rel_adj[rb0 + tt - na_r];
+                const int4 id = P.rel_idx[r];
+                if (id.x == a || id.y == a || id.z == a || id.w == a) r = -1;
+            }
+            float pd, pe;
+            rel_pen<CPW>(P, Pc, r >= 0 ? r : 0, pd, pe);
+            if (r >= 0) {
+                const float2 old = PRc[r * CPW];
+                PRc[r * CPW] = make_float2(pd, pe);
+                if (slot == 0) { stash.r0 = r; stash.o0 = old; }
+                else if (slot == 1) { stash.r1 = r; stash.o1 = old; }
+                else stash.overflow = 1;
+            }
+        }
+        if (tmax > 2 * G) stash.overflow = -group_min_int<G, STR>(-stash.overflow);
+    }
+    __syncwarp();
+    float pw = 0.f, pa = 0.f;
+#pragma unroll 1
+    for (int r = g; r < R; r += G) {
+        const float2 v = PRc[r * CPW];
+        pw += v.x;
+        pa += v.y;
+    }
+    pw_total = group_sum<G, STR>(pw);
+    pa_total = group_sum<G, STR>(pa);
+}
+
+// The proposal was rejected and Pc holds the current layout again: put the memo back.
+template <int G>
+__device__ __forceinline__ void rel_memo_restore(const SmemProblem &P, const float4 *Pc, float2 *PRc, const int g, const int a, const int b,
+                                                 const RelMemoStash &stash)
+{
+    constexpr int CPW = 32 / G;
+    if (stash.r0 >= 0) PRc[stash.r0 * CPW] = stash.o0;
+    if (stash.r1 >= 0) PRc[stash.r1 * CPW] = stash.o1;
+    if (stash.overflow) {
+        for (int which = 0; which < 2; which++) {
+            const int m = which ? b : a;
+            if (m < 0) continue;
+            for (int t = P.rel_adj_off[m] + g; t < P.rel_adj_off[m + 1]; t += G) {
+                const int r = P.rel_adj[t];
+                float pd, pe;
+                rel_pen<CPW>(P, Pc, r, pd, pe);
+                PRc[r * CPW] = make_float2(pd, pe);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // MH_EVAL_MEMO: full evaluation, bit for bit, at a fraction of the work.  Every term of the proposal is
 // what eval_terms computes for it -- the same values, added in the same order:
 //   symmetry       the exact memo above (row minima; min is exact);
@@ -506,9 +594,7 @@ __device__ __forceinline__ void delta_commit(const SmemProblem &P, const WarpSta
 // Nothing is a running sum, so nothing drifts and there is no periodic rebuild.
 template <int G> struct ExactStash {
     static constexpr int JOBS = (4 + G - 1) / G;   // surface jobs per lane (4 in all: objects a, b, clearances a, b)
-    int r0, r1;           // relationships this lane overwrote in the PR memo ...
-    float2 o0, o1;        // ... and their penalties in the current layout (restored on rejection)
-    int overflow;         // some lane of the group overwrote more than two: rejection recomputes
+    RelMemoStash rel;     // the PR entries this lane overwrote
     float sv_old[JOBS];   // the SV entries this lane overwrote
 };
 
@@ -530,7 +616,7 @@ __device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpStat
     constexpr int CPW = WS::CPW;
     constexpr unsigned FULL = 0xffffffffu;
     const mhProblemHeader *h = P.h;
-    const int n = h->n, C = h->C, R = h->R;
+    const int n = h->n, C = h->C;
     const float4 *Pc = S.P4 + c, *CBc = S.CB + c;
     const bool mvb = b >= 0;
     const bool any_b = __any_sync(FULL, mvb);
@@ -596,37 +682,9 @@ __device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpStat
         }
     }
 
-    // ---- relationships that name a moved object, dealt round-robin to the lanes (as in delta_eval) --------
-    stash.r0 = stash.r1 = -1;
-    stash.overflow = 0;
-    {
-        const int ra0 = P.rel_adj_off[a], na_r = P.rel_adj_off[a + 1] - ra0;
-        const int rb0 = mvb ? P.rel_adj_off[b] : 0, nb_r = mvb ? P.rel_adj_off[b + 1] - rb0 : 0;
-        const int tot = na_r + nb_r;
-        const int tmax = __reduce_max_sync(FULL, tot);
-        int slot = 0;
-        for (int tt = g; tt < tmax; tt += G, slot++) {
-            int r = -1;
-            if (tt < na_r) {
-                r = P.rel_adj[ra0 + tt];
-            } else if (tt < tot) {
-                r = P.rel_adj[rb0 + tt - na_r];
-                const int4 id = P.rel_idx[r];
-                if (id.x == a || id.y == a || id.z == a || id.w == a) r = -1;
-            }
-            float pd, pe;
-            rel_pen<CPW>(P, Pc, r >= 0 ? r : 0, pd, pe);
-            if (r >= 0) {
-                const float2 old = D.pr(r, c);
-                D.pr(r, c) = make_float2(pd, pe);
-                if (slot == 0) { stash.r0 = r; stash.o0 = old; }
-                else if (slot == 1) { stash.r1 = r; stash.o1 = old; }
-                else stash.overflow = 1;
-            }
-        }
-        if (tmax > 2 * G) stash.overflow = -group_min_int<G, kDeltaStr>(-stash.overflow);
-    }
-    __syncwarp();                                               // S.CB, SV and PR are read by other lanes below
+    // ---- relationships: memo update and the two sums (synchronises the warp: S.CB and SV, written above,
+    //      are read by other lanes below) -------------------------------------------------------------------
+    rel_memo_eval<G, kDeltaStr>(P, Pc, D.PR + c, g, a, b, stash.rel, t.pw, t.pa);
 
     // ---- clearance ---------------------------------------------------------------------------------------------
     if (MODE == kModeExactCR) {
@@ -643,7 +701,7 @@ __device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpStat
     }
     // ---- one pass over the lane's rows, every sum in eval_terms' order -------------------------------------
     {
-        float surf = 0.f, clr = 0.f, vbx = 0.f, vby = 0.f, focal = 0.f, pw = 0.f, pa = 0.f;
+        float surf = 0.f, clr = 0.f, vbx = 0.f, vby = 0.f, focal = 0.f;
 #pragma unroll kDuSum
         for (int k = g; k < C; k += G)
             surf += D.sv(n + k, c);
@@ -669,14 +727,6 @@ __device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpStat
             }
             clr += acc;
         }
-#pragma unroll kDuSum
-        for (int r = g; r < R; r += G) {
-            const float2 v = D.pr(r, c);
-            pw += v.x;
-            pa += v.y;
-        }
-        t.pw = group_sum<G, kDeltaStr>(pw);
-        t.pa = group_sum<G, kDeltaStr>(pa);
         t.vbx = group_sum<G, kDeltaStr>(vbx);
         t.vby = group_sum<G, kDeltaStr>(vby);
         t.focal = group_sum<G, kDeltaStr>(focal);
@@ -722,20 +772,7 @@ __device__ __forceinline__ void exact_reject(const SmemProblem &P, const WarpSta
         const int slot = job < 4 ? sv_slot(job, a, b, n, C) : -1;
         if (slot >= 0) D.sv(slot, c) = stash.sv_old[q];
     }
-    if (stash.r0 >= 0) D.pr(stash.r0, c) = stash.o0;
-    if (stash.r1 >= 0) D.pr(stash.r1, c) = stash.o1;
-    if (stash.overflow) {
-        for (int which = 0; which < 2; which++) {
-            const int m = which ? b : a;
-            if (m < 0) continue;
-            for (int t = P.rel_adj_off[m] + g; t < P.rel_adj_off[m + 1]; t += G) {
-                const int r = P.rel_adj[t];
-                float pd, pe;
-                rel_pen<CPW>(P, Pc, r, pd, pe);
-                D.pr(r, c) = make_float2(pd, pe);
-            }
-        }
-    }
+    rel_memo_restore<G>(P, Pc, D.PR + c, g, a, b, stash.rel);
 }
 
 } // namespace mh

@@ -571,6 +571,33 @@ def test_default_mode_switches_to_the_memo_transparently(kernel):
         assert pa.tobytes() == pb.tobytes() and ca.tobytes() == cb.tobytes(), n
 
 
+def test_small_rooms_default_and_memo_equal_the_plain_scan(kernel):
+    """Below 32 objects MH_EVAL_FULL runs the plain scan (a relationship memo inside the scan kernel was
+    tried and lost: with 16 chains per warp some chain always has many touched relationships); whatever it
+    runs, and the memo form when asked for, must return the plain scan's traces, layouts and costs for
+    every lane width, with relationship hubs (more touched relationships than stash slots), frozen
+    objects, best tracking, annealing, across launches."""
+    rooms = [S.make_config(1), S.make_config(2), S.make_room(24, 12, 40, 7.0, 5.0, 321), S.make_room(5, 2, 30, 4.0, 4.0, 322)]
+    rooms += [S.make_wild_room(n, C, R, 900 + n) for n, C, R in ((3, 1, 12), (17, 9, 25), (31, 31, 50), (9, 0, 64))]
+    for ri, room in enumerate(rooms):
+        for lanes in (1, 2, 4, 16):
+            out = []
+            for mode in (3, 0, 2):
+                try:
+                    ctx = kernel.create(room, 40, seed=ri, lanes_per_chain=lanes, eval_mode=mode, result_mode=ri % 2, beta_start=1.0,
+                                        beta_end=6.0, schedule=1, schedule_length=200)
+                except pkg.KernelError as e:                    # 32 chains per warp with all memos: 31 objects do not fit
+                    assert mode == 2 and lanes == 1 and "shared memory" in str(e), e
+                    continue
+                with ctx:
+                    tr = ctx.run_traced(120)
+                    ctx.run(80)
+                    out.append((tr, *ctx.results()))
+            for o in out[1:]:
+                assert out[0][0].tobytes() == o[0].tobytes(), (ri, lanes)
+                assert out[0][1].tobytes() == o[1].tobytes() and out[0][2].tobytes() == o[2].tobytes(), (ri, lanes)
+
+
 def test_memo_and_delta_on_wild_rooms_every_lane_width(kernel, oracle):
     """The memo form against the full scan, bit for bit, and the delta form against a fresh evaluation, on
     rooms with shared clearance sources, relationship hubs, frozen objects and odd sizes, for every lane
