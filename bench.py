@@ -426,11 +426,11 @@ def main():
                         "call": "KernelWrapperEx (host buffers in, malloc'd result block out)"},
                 "gpu_launches": int(l1 - l0), "roofline": roofline, "clocks": clocks,
                 "best": {"global_chain": int(best[0]), "totalCosts": float(best[1])}, "device": info["name"]}
-        if not args.no_extras:
+        if not args.no_extras and world == 1:                    # the side measurements run at N=1 only
             line["other_configs_kernel_only"] = other_configs(k, pkg)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(room)
-        if not args.no_ref_gpu:
+        if not args.no_ref_gpu and world == 1:
             try:
                 if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libKernel_ref_nb.so")):
                     v_wall, v_dev, _ = reference_gpu(args.config, args.ref_chains, args.ref_iterations, 1, 1, timeout_s=120)
