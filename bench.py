@@ -127,9 +127,29 @@ def cpu_baseline(room, target_seconds=12.0):
     _, _, secs, th = o.run(room, chains, 400, seed=1, timed=True, threads=threads)         # calibrate
     rate = chains * 400 / max(secs, 1e-6)
     iters = max(20, int(rate * target_seconds / chains))
-    _, _, secs, th = o.run(room, chains, iters, seed=1, timed=True, threads=threads)
+    _, costs, secs, th = o.run(room, chains, iters, seed=1, timed=True, threads=threads)
     return {"value": chains * iters / secs, "unit": UNIT, "cores": th, "kind": "port",
-            "sample": f"{chains} chains x {iters} iterations of the same room ({secs:.1f} s), {flags} -ffp-contract=off, OpenMP"}
+            "sample": f"{chains} chains x {iters} iterations of the same room ({secs:.1f} s), {flags} -ffp-contract=off, OpenMP",
+            "seconds": secs, "best_totalCosts": float(costs["totalCosts"].max()),
+            "median_final_totalCosts": float(np.median(costs["totalCosts"]))}
+
+
+def time_to_best_cost(k, room, chains, target, epoch=50, max_iterations=60000):
+    """The second half of BASELINE.json's metric: wall time until the global best totalCosts (the sampler
+    maximises it, quirk Q10) first reaches `target`, checked every `epoch` iterations with the device
+    arg-max (KernelBest: one 8-byte read per check).  Starts from the caller's layout, context creation
+    included."""
+    t0 = time.perf_counter()
+    done, best = 0, -1e30
+    with k.create(room, chains, seed=424242) as ctx:
+        while done < max_iterations:
+            ctx.run(epoch)
+            done += epoch
+            best = ctx.best()[1]
+            if best >= target:
+                return {"seconds": time.perf_counter() - t0, "iterations_per_chain": done, "chains": chains, "reached": True,
+                        "best_totalCosts": best}
+    return {"seconds": time.perf_counter() - t0, "iterations_per_chain": done, "chains": chains, "reached": False, "best_totalCosts": best}
 
 
 def reference_gpu(config_id, chains, iters, steps, warmup, timeout_s=300):
@@ -429,7 +449,21 @@ def main():
         if not args.no_extras and world == 1:                    # the side measurements run at N=1 only
             line["other_configs_kernel_only"] = other_configs(k, pkg)
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(room)
+            cb = cpu_baseline(room)
+            line["cpu_baseline"] = cb
+            # time-to-best-cost: how long until the GPU run's global best reaches what the CPU port's chains
+            # reached (their best, and the median of their finals) in its cb["seconds"] of host time
+            ttb = {"cpu_seconds": cb["seconds"],
+                   "note": "targets = totalCosts reached by the CPU port's sample (best of its chains / median of its chains' finals) in "
+                           "cpu_seconds of host time; GPU: wall time from KernelCreate until the device arg-max over the chains reaches "
+                           "it, checked every 200 iterations.  Reaching a given cost is a matter of iterations per chain, so fewer "
+                           "chains (wider lane groups, an under-filled but low-latency machine) get there first"}
+            for name in ("best_totalCosts", "median_final_totalCosts"):
+                ttb["to_cpu_" + name] = {"target": cb[name],
+                                         "runs": [time_to_best_cost(k, room, ch, cb[name], epoch=200) for ch in (1024, 4096, args.chains)]}
+                ttb["to_cpu_" + name]["seconds"] = min(r["seconds"] for r in ttb["to_cpu_" + name]["runs"] if r["reached"]) \
+                    if any(r["reached"] for r in ttb["to_cpu_" + name]["runs"]) else None
+            line["time_to_best_cost"] = ttb
         if not args.no_ref_gpu and world == 1:
             try:
                 if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libKernel_ref_nb.so")):

@@ -326,6 +326,9 @@ static int choose_lanes(int n, int C, int R, int smem_words, int n_chains, int r
         const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, eval_mode, 4);
         if (bytes < 0 || bytes > max_block) continue;
         if (requested == G) return G;
+        /* one lane per chain: the 32 lanes of a warp load 32 different float4s per column (4 shared-memory
+         * wavefronts instead of a broadcast), which binds from ~20 objects (measured at n=24: 1.13e9 against 1.52e9) */
+        if (G == 1 && n >= 20 && best > 0) continue;
         int blocks_per_sm = max_sm / (bytes + 1024);
         if (blocks_per_sm > MH_MAX_BLOCKS_PER_SM) blocks_per_sm = MH_MAX_BLOCKS_PER_SM; /* register-limited */
         if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -334,7 +337,9 @@ static int choose_lanes(int n, int C, int R, int smem_words, int n_chains, int r
         const double warps_total = ceil((double)n_chains / cpw);
         double per_sm = warps_total / (double)sms;
         if (per_sm > cap_warps) per_sm = cap_warps;
-        const double cover = per_sm >= 18.0 ? 1.0 : per_sm / 18.0;
+        /* latency is covered from ~12 resident warps per SM (measured: n=8 runs best with 1 lane per chain at 14
+         * warps/SM, n=16 with 16384 chains best with 4 lanes at 14 warps/SM, not with 8 at 28) */
+        const double cover = per_sm >= 12.0 ? 1.0 : per_sm / 12.0;
         const double rows = ceil((double)n / G);
         /* warp instructions of the whole job: with chains to spare this is proportional to G (the old form of
          * the model); with fewer chains than a warp holds it is not -- one chain is one warp for every G, and
