@@ -733,6 +733,16 @@ def test_plain_c_caller_gets_the_same_bits(kernel, tmp_path, monkeypatch):
     assert costs["totalCosts"].min() > 3921.0        # the sampler climbs from the fixture's 3921.14
 
 
+def test_full_size_memo_equals_scan(kernel):
+    """At BASELINE sizes: the default (memo form) and the plain scan return the same bytes for all 65536
+    chains of config 3 after 3000 iterations, and for 8192 chains of config 4 after 300."""
+    for cid, chains, iters, lanes in ((3, 65536, 3000, 8), (4, 8192, 300, 32)):
+        room = S.make_config(cid)
+        pa, ca = kernel.wrapper_ex(room, chains, iters, seed=2026, lanes_per_chain=lanes)
+        pb, cb = kernel.wrapper_ex(room, chains, iters, seed=2026, lanes_per_chain=lanes, eval_mode=3)
+        assert pa.tobytes() == pb.tobytes() and ca.tobytes() == cb.tobytes(), cid
+
+
 def test_full_size_properties_config4(kernel, oracle):
     """BASELINE config 4 at its full chain count (262144 chains x 200 objects = 1.26 GB of results),
     few iterations: size-independent properties -- every chain inside the room, reported costs are the
