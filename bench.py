@@ -4,6 +4,7 @@ headline metric, on the 50-object living room (config 3: n=50, C=25, R=50, 65536
 10000 iterations, all cost terms, beta = 2).
 
   python bench.py --gpus N --steps K --warmup W            this repo's sm_100a path
+  python bench.py --eval-mode 3 ...                         the same with the plain scan (every term from scratch)
   python bench.py --impl reference ...                      the reference's own kernel, rebuilt for
                                                             sm_100 from /root/reference (oracle/_ref)
 
@@ -318,6 +319,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--eval-mode", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="mhOptions.eval_mode of the timed runs: 0 library default (memo form from 32 objects, bit-identical to 3), "
+                         "3 plain scan (every term from scratch), 1 delta evaluation, 2 memo form")
     ap.add_argument("--no-extras", action="store_true", help="skip the quick kernel-only rates of the other rooms")
     args = ap.parse_args()
 
@@ -361,7 +365,7 @@ def main():
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
-    ctx = k.create(room, args.chains, seed=20261018, chain_offset=offset, lanes_per_chain=args.lanes)
+    ctx = k.create(room, args.chains, seed=20261018, chain_offset=offset, lanes_per_chain=args.lanes, eval_mode=args.eval_mode)
     ctx.set_stream(stream)
 
     def step():
@@ -396,11 +400,12 @@ def main():
     in_bytes = sum(a.nbytes for a in (room.rss, room.rsa, room.cfg, room.clearances, room.offlimits, room.vertices,
                                       room.surfaceRectangle, room.srf)) + 24
     out_bytes = args.chains * n * 24 + args.chains * 32
-    k.wrapper_ex(room, args.chains, max(1, args.iterations // 100), seed=7, chain_offset=offset)   # warm
+    k.wrapper_ex(room, args.chains, max(1, args.iterations // 100), seed=7, chain_offset=offset, eval_mode=args.eval_mode)   # warm
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
-        res, pts, costs = k.wrapper_ex_raw(room, args.chains, args.iterations, seed=7 + s, chain_offset=offset, lanes_per_chain=args.lanes)
+        res, pts, costs = k.wrapper_ex_raw(room, args.chains, args.iterations, seed=7 + s, chain_offset=offset, lanes_per_chain=args.lanes,
+                                           eval_mode=args.eval_mode)
         e2e_best = float(costs["totalCosts"].max())        # the caller reads the result in place ...
         k.free(res)                                        # ... and hands it back
     barrier()
@@ -419,7 +424,7 @@ def main():
         achieved = per_gpu_rate * f_live / 1e12
         scan_rate = quick_rate(k, room, args.chains, max(200, min(2000, args.iterations)), eval_mode=3, lanes_per_chain=args.lanes)
         roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                    "effective": True,
+                    "effective": args.eval_mode != 3 and n >= 32,
                     "effective_note": "algorithmic flops of a full evaluation x proposals/s: the default kernel returns the full evaluation's "
                                       "bits but executes a fraction of its arithmetic (exact memos); the plain scan, which executes all of it, "
                                       "is in full_scan",
@@ -429,7 +434,9 @@ def main():
                     "traffic_note": f"bytes per launch at 65536 chains from profiles/{PROFILE_FILE} (result block; independent of the iteration count)",
                     "flops_per_proposal": {"live": f_live, "contract": f_contract},
                     "achieved_contract": per_gpu_rate * f_contract / 1e12, "frac_contract": per_gpu_rate * f_contract / 1e12 / peak_tflops,
-                    "kernel": "mh_delta_kernel<8, exact> (MH_EVAL_FULL in its memo form)" if n >= 32 else "mh_chain_kernel",
+                    "kernel": {0: "mh_delta_kernel<8, exact> (MH_EVAL_FULL in its memo form)" if n >= 32 else "mh_chain_kernel",
+                               1: "mh_delta_kernel<., delta> (MH_EVAL_DELTA)", 2: "mh_delta_kernel<., exact> (MH_EVAL_MEMO)",
+                               3: "mh_chain_kernel (MH_EVAL_FULL_SCAN)"}[args.eval_mode],
                     "kernel_ms_per_launch": kernel_max * 1e3 / args.steps,
                     "peak_source": f"FP32 pipe = {info['sm_count']} SMs x 128 lanes x 2 x {sm_max_mhz:.0f} MHz (sm_max_mhz of "
                                    + ("MEASURED_PEAKS.json" if peaks.get("sm_max_mhz") else "nvidia-smi") + "); HBM is not the bound: "
@@ -439,7 +446,10 @@ def main():
                 "ms_per_step": wall_max * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"config {args.config} ({room.name}): n={n} C={room.C} R={room.R}, {args.chains} chains/GPU x {args.iterations} iterations, all cost terms, beta=2",
-                           "evaluation": "MH_EVAL_FULL (library default): every proposal's full cost, bit-identical to the plain re-evaluation, computed through exact memos",
+                           "evaluation": {0: "MH_EVAL_FULL (library default): every proposal's full cost, bit-identical to the plain re-evaluation, computed through exact memos",
+                                          1: "MH_EVAL_DELTA: incremental running sums, statistically equivalent to the full evaluation",
+                                          2: "MH_EVAL_MEMO: the full evaluation's bits through exact memos",
+                                          3: "MH_EVAL_FULL_SCAN: every live cost term of every proposal from scratch"}[args.eval_mode],
                            "chains_total": total_chains, "lanes_per_chain": args.lanes or "auto", "parallelism": f"chains sharded over {world} GPU(s), NCCL arg-best",
                            "l2": "256 MiB memset between steps; the chain state lives in shared memory"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
