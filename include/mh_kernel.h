@@ -196,6 +196,12 @@ MH_API int KernelReset(mhContext *ctx);
  * betas.  Betas move, layouts never cross the link: 8 bytes per chain per exchange. */
 MH_API int KernelTemperingState(mhContext *ctx, void **d_totals, void **d_betas);
 MH_API int KernelTemperingExchange(mhContext *ctx, const void *d_all_totals, const void *d_all_betas);
+/* Replica-exchange bookkeeping since creation / the last KernelReset, for tuning a ladder: for every pair of
+ * neighbouring rungs (r, r+1), r = 0 .. rungs-2, how many exchanges THIS context's chains attempted as the
+ * pair's lower member and how many were accepted (sum over the ranks for a ladder spread over GPUs).  A
+ * pair that hardly ever swaps is a gap in the ladder; one that always swaps is a rung too many.  Returns
+ * rungs-1 or -1. */
+MH_API int KernelTemperingStats(mhContext *ctx, long long *attempts, long long *accepted);
 /* Milliseconds the device spent in the MH kernels since creation (CUDA events) and how many
  * kernels were launched. */
 MH_API int KernelStats(mhContext *ctx, double *kernel_ms, long long *launches);

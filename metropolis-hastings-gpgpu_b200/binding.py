@@ -17,7 +17,7 @@ _P = C.c_void_p
 
 EXPORTS = ("KernelWrapper", "KernelWrapperEx", "KernelFree", "KernelLastError", "KernelEvalCosts", "KernelCreate", "KernelRun",
            "KernelRunTraced", "KernelSynchronize", "KernelResults", "KernelDeviceResults", "KernelSetStream", "KernelBest",
-           "KernelStats", "KernelDestroy", "KernelDeviceInfo", "KernelBestKey", "KernelDecodeBestKey", "KernelReset", "KernelTrim", "KernelTemperingState", "KernelTemperingExchange", "KernelTopK", "KernelTopKDistinct")
+           "KernelStats", "KernelDestroy", "KernelDeviceInfo", "KernelBestKey", "KernelDecodeBestKey", "KernelReset", "KernelTrim", "KernelTemperingState", "KernelTemperingExchange", "KernelTopK", "KernelTopKDistinct", "KernelTemperingStats")
 
 
 class KernelError(RuntimeError):
@@ -73,6 +73,7 @@ class Kernel:
             lib.KernelTopKDistinct.argtypes = [_P, C.c_int, C.c_float, C.c_float, _P, _P]
             lib.KernelTemperingState.argtypes = [_P, C.POINTER(_P), C.POINTER(_P)]
             lib.KernelTemperingExchange.argtypes = [_P, _P, _P]
+            lib.KernelTemperingStats.argtypes = [_P, _P, _P]
             lib.KernelDecodeBestKey.argtypes = [C.c_longlong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]
             lib.KernelDecodeBestKey.restype = None
             Kernel._lib = lib
@@ -238,6 +239,14 @@ class Context:
     def tempering_exchange(self, d_all_totals, d_all_betas):
         if self.k.lib.KernelTemperingExchange(self.h, _P(d_all_totals), _P(d_all_betas)) != 0:
             self.k._fail("KernelTemperingExchange")
+
+    def tempering_stats(self, rungs):
+        """(attempts, accepted) per pair of neighbouring rungs, as counted by this context's chains."""
+        att = np.zeros(rungs - 1, np.int64)
+        acc = np.zeros(rungs - 1, np.int64)
+        if self.k.lib.KernelTemperingStats(self.h, _ptr(att), _ptr(acc)) != rungs - 1:
+            self.k._fail("KernelTemperingStats")
+        return att, acc
 
     def reset(self):
         if self.k.lib.KernelReset(self.h) != 0:

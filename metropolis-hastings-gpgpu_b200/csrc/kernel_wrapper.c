@@ -281,7 +281,7 @@ struct mhContext {
     void *d_problem;
     float *d_x, *d_y, *d_rot, *d_cur, *d_best, *d_beta, *d_beta_snap;
     uint16_t *d_perm;
-    void *d_points, *d_costs, *d_scratch;
+    void *d_points, *d_costs, *d_scratch, *d_exch_stats;
     void *stream;
     int own_stream;
     uint64_t it_done;  /* iterations already run (relative to opt.iteration_offset) */
@@ -405,7 +405,7 @@ static void ctx_free(mhContext *c)
     void *st = c->stream;
     mhdev_free(c->d_problem, st); mhdev_free(c->d_x, st); mhdev_free(c->d_y, st); mhdev_free(c->d_rot, st); mhdev_free(c->d_cur, st);
     mhdev_free(c->d_best, st); mhdev_free(c->d_beta, st); mhdev_free(c->d_perm, st); mhdev_free(c->d_points, st);
-    mhdev_free(c->d_costs, st); mhdev_free(c->d_scratch, st); mhdev_free(c->d_beta_snap, st);
+    mhdev_free(c->d_costs, st); mhdev_free(c->d_scratch, st); mhdev_free(c->d_beta_snap, st); mhdev_free(c->d_exch_stats, st);
     for (int i = 0; i < c->n_ev; i++) { mhdev_event_destroy(c->ev[i].e0); mhdev_event_destroy(c->ev[i].e1); }
     free(c->ev);
     if (c->own_stream) mhdev_stream_destroy(c->stream);
@@ -535,6 +535,10 @@ MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationship
     CU(mhdev_malloc((void **)&c->d_best, 4 * (size_t)nChains, c->stream));
     CU(mhdev_malloc((void **)&c->d_beta, 4 * (size_t)nChains, c->stream));
     CU(mhdev_malloc((void **)&c->d_beta_snap, 4 * (size_t)nChains, c->stream));
+    if (c->opt.tempering_rungs > 1) {
+        CU(mhdev_malloc(&c->d_exch_stats, 16 * (size_t)c->opt.tempering_rungs, c->stream));
+        CU(mhdev_memset(c->d_exch_stats, 0, 16 * (size_t)c->opt.tempering_rungs, c->stream));
+    }
     CU(mhdev_malloc(&c->d_points, sizeof(point) * cn, c->stream));
     CU(mhdev_malloc(&c->d_costs, sizeof(resultCosts) * (size_t)nChains, c->stream));
     CU(mhdev_malloc(&c->d_scratch, 64, c->stream));
@@ -655,7 +659,7 @@ static int run_iterations(mhContext *c, int iterations, mhTraceEntry *trace)
                 CU(mhdev_d2d(c->d_beta_snap, c->d_beta, 4 * (size_t)c->n_chains, c->stream));
                 CU(mhdev_launch_exchange(c->n_chains, c->opt.chain_offset, 1, c->opt.tempering_rungs, gnow / ex, gnow - 1,
                                          c->opt.seed, c->d_cur, c->d_beta_snap, c->opt.chain_offset, 1, (uint64_t)c->n_chains,
-                                         c->d_beta, c->stream));
+                                         c->d_beta, c->d_exch_stats, c->stream));
                 c->launches++;
             }
         }
@@ -894,6 +898,7 @@ MH_API int KernelReset(mhContext *ctx)
         int prev = -1, rc = -1;
         CU(enter_device(ctx->device, &prev));
         CU(init_betas(ctx));
+        CU(mhdev_memset(ctx->d_exch_stats, 0, 16 * (size_t)ctx->opt.tempering_rungs, ctx->stream));
         rc = 0;
     fail:
         if (prev >= 0) leave_device(ctx->device, prev);
@@ -922,10 +927,33 @@ MH_API int KernelTemperingExchange(mhContext *ctx, const void *d_all_totals, con
     CU(enter_device(ctx->device, &prev));
     CU(mhdev_launch_exchange(ctx->n_chains, ctx->opt.chain_offset, ctx->opt.chain_stride, ctx->opt.tempering_rungs, gnow / ex, gnow - 1,
                              ctx->opt.seed, (const float *)d_all_totals, (const float *)d_all_betas, 0, ctx->opt.chain_stride,
-                             (uint64_t)ctx->n_chains, ctx->d_beta, ctx->stream));
+                             (uint64_t)ctx->n_chains, ctx->d_beta, ctx->d_exch_stats, ctx->stream));
     ctx->launches++;
     rc = 0;
 fail:
+    if (prev >= 0) leave_device(ctx->device, prev);
+    return rc;
+}
+
+MH_API int KernelTemperingStats(mhContext *ctx, long long *attempts, long long *accepted)
+{
+    int prev = -1, rc = -1;
+    unsigned long long *h = NULL;
+    g_err[0] = 0;
+    if (!ctx || ctx->opt.tempering_rungs <= 1) { set_err("", "context has no tempering ladder", 0); return -1; }
+    const int pairs = ctx->opt.tempering_rungs - 1;
+    h = (unsigned long long *)malloc(16 * (size_t)ctx->opt.tempering_rungs);
+    if (!h) { set_err("", "out of host memory", 0); return -1; }
+    CU(enter_device(ctx->device, &prev));
+    CU(mhdev_d2h(h, ctx->d_exch_stats, 16 * (size_t)ctx->opt.tempering_rungs, ctx->stream));
+    CU(mhdev_stream_sync(ctx->stream));
+    for (int r = 0; r < pairs; r++) {
+        if (attempts) attempts[r] = (long long)h[2 * r];
+        if (accepted) accepted[r] = (long long)h[2 * r + 1];
+    }
+    rc = pairs;
+fail:
+    free(h);
     if (prev >= 0) leave_device(ctx->device, prev);
     return rc;
 }

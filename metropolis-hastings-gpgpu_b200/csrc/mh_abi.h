@@ -99,7 +99,8 @@ int mhdev_launch_score(const void *d_problem, int smem_words, int n, int C, int 
  * after an all-gather over gather_stride ranks (gather_stride = 1: plain global order). */
 int mhdev_launch_exchange(int n_chains, uint64_t chain_offset, uint64_t chain_stride, int rungs, uint64_t epoch,
                           uint64_t it_last, uint64_t seed, const float *d_all_total, const float *d_all_beta,
-                          uint64_t gather_base, uint64_t gather_stride, uint64_t gather_local, float *d_beta, void *stream);
+                          uint64_t gather_base, uint64_t gather_stride, uint64_t gather_local, float *d_beta,
+                          void *d_stats /* uint64[2*rungs] {attempts, accepted} per pair (lower rung), or NULL */, void *stream);
 /* arg-max of totalCosts over the context's chains: d_out = {float total, int32 chain}. */
 int mhdev_launch_argmax(const void *d_costs, int n_chains, void *d_out, void *stream);
 /* Distinct suggestions: d_mind[chain] = min(d_mind[chain], distance of the chain's layout to ref_chain's);

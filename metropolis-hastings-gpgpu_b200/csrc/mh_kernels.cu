@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(THREADS) mh_score_kernel(const float *__restri
 __global__ void mh_exchange_kernel(int n_chains, uint64_t chain_offset, uint64_t chain_stride, int rungs, uint64_t epoch,
                                    uint64_t it_last, uint64_t seed, const float *__restrict__ all_total,
                                    const float *__restrict__ all_beta, uint64_t gather_base, uint64_t gather_stride,
-                                   uint64_t gather_local, float *__restrict__ beta)
+                                   uint64_t gather_local, float *__restrict__ beta, unsigned long long *__restrict__ stats)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_chains) return;
@@ -557,6 +557,10 @@ __global__ void mh_exchange_kernel(int n_chains, uint64_t chain_offset, uint64_t
     const double ba = (double)all_beta[ilo], bb = (double)all_beta[ihi];
     const float pacc = fminf(1.0f, (float)exp((ba - bb) * (Ea - Eb)));
     if (u < pacc) beta[i] = (float)(r == lo_r ? bb : ba);
+    if (stats && r == lo_r) {                                   // the pair's lower member keeps the books: {attempts, accepted}
+        atomicAdd(&stats[2 * lo_r], 1ull);
+        if (u < pacc) atomicAdd(&stats[2 * lo_r + 1], 1ull);
+    }
 }
 
 __global__ void mh_argmax_kernel(const Costs8 *__restrict__ costs, int n, float *out_total, int *out_idx)
@@ -771,12 +775,12 @@ int mhdev_launch_score(const void *d_problem, int smem_words, int n, int C, int 
 
 int mhdev_launch_exchange(int n_chains, uint64_t chain_offset, uint64_t chain_stride, int rungs, uint64_t epoch, uint64_t it_last,
                           uint64_t seed, const float *d_all_total, const float *d_all_beta, uint64_t gather_base,
-                          uint64_t gather_stride, uint64_t gather_local, float *d_beta, void *stream)
+                          uint64_t gather_stride, uint64_t gather_local, float *d_beta, void *d_stats, void *stream)
 {
     if (n_chains <= 0) return 0;
     mh::mh_exchange_kernel<<<(n_chains + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         n_chains, chain_offset, chain_stride, rungs, epoch, it_last, seed, d_all_total, d_all_beta, gather_base, gather_stride,
-        gather_local, d_beta);
+        gather_local, d_beta, static_cast<unsigned long long *>(d_stats));
     return (int)cudaGetLastError();
 }
 

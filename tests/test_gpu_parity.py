@@ -409,6 +409,35 @@ def test_parallel_tempering_matches_oracle(kernel, oracle):
     assert stats.ks_2samp(ck["totalCosts"], co["totalCosts"]).pvalue > 0.01
 
 
+def test_tempering_exchange_statistics(kernel):
+    """KernelTemperingStats: every exchange epoch tries the pairs (r, r+1) with r of the epoch's parity once
+    per ladder; the accepted counts must equal the beta swaps seen in the trace; KernelReset clears them."""
+    room = S.make_config(1)
+    rungs, ex, ladders, iters = 4, 20, 16, 400
+    with kernel.create(room, rungs * ladders, seed=21, beta_start=0.5, beta_end=8.0, tempering_rungs=rungs, exchange_interval=ex) as ctx:
+        tr = ctx.run_traced(iters)
+        ctx.run(ex)                                               # ends on an exchange boundary: the epoch at iters is applied
+        att, acc = ctx.tempering_stats(rungs)
+        epochs = np.arange(1, iters // ex + 2)                   # exchanges after iterations 20, 40, ..., 420
+        expect = np.array([np.sum(epochs % 2 == r % 2) * ladders for r in range(rungs - 1)])
+        assert np.array_equal(att, expect), (att, expect)
+        assert np.all(acc <= att) and acc.sum() > 0
+        # swaps visible in the trace: beta of a chain position changes exactly at an accepted exchange of its pair
+        beta = tr["beta"]                                        # [iteration][chain]
+        swaps = np.zeros(rungs - 1, np.int64)
+        for e in range(1, iters // ex):                          # epochs whose effect is inside the traced window
+            before, after = beta[e * ex - 1], beta[e * ex]
+            for l in range(ladders):
+                for r in range(rungs - 1):
+                    i = l * rungs + r
+                    if r % 2 == e % 2 and before[i] != after[i] and after[i] == before[i + 1]:
+                        swaps[r] += 1
+        assert np.all(swaps <= acc) and np.all(acc - swaps <= 2 * ladders)   # (the last two epochs are outside the trace)
+        ctx.reset()
+        att, acc = ctx.tempering_stats(rungs)
+        assert att.sum() == 0 and acc.sum() == 0
+
+
 def test_tempering_resume_and_sharding(kernel):
     room = S.make_config(1)
     opts = dict(seed=5, beta_start=0.5, beta_end=8.0, tempering_rungs=4, exchange_interval=25, lanes_per_chain=2)
