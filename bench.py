@@ -9,7 +9,7 @@ headline metric, on the 50-object living room (config 3: n=50, C=25, R=50, 65536
                                                             sm_100 from /root/reference (oracle/_ref)
 
 One step = one pass of the hot path over the whole batch: every chain runs `iterations` MH steps
-from the caller's layout.  The library's default evaluation (MH_EVAL_FULL) runs, from 32 objects up, in
+from the caller's layout.  The library's default evaluation (MH_EVAL_FULL) runs, from 28 objects up, in
 its memo form: every proposal's costs, every accept decision and every returned bit equal the plain
 full re-evaluation's (tested), at a fraction of the work; the plain scan's rate is reported beside it.  `value` is timed with the problem and chain state already resident in
 HBM (KernelCreate once, then KernelReset + KernelRun per step, CUDA events around the kernel);
@@ -195,7 +195,7 @@ def other_configs(k, pkg):
         out[f"config{cid}"] = e
     room = pkg.synth.make_config(3)
     out["config3_delta_eval"] = quick_rate(k, room, 65536, 512, eval_mode=1)
-    out["note"] = ("full_eval = the library default (bit-identical memo form from 32 objects up); full_eval_plain_scan = every term "
+    out["note"] = ("full_eval = the library default (bit-identical memo form from 28 objects up); full_eval_plain_scan = every term "
                    "from scratch; delta_eval = incremental running sums, statistically equivalent (MH_EVAL_DELTA)")
     return out
 
@@ -320,7 +320,7 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--eval-mode", type=int, default=0, choices=[0, 1, 2, 3],
-                    help="mhOptions.eval_mode of the timed runs: 0 library default (memo form from 32 objects, bit-identical to 3), "
+                    help="mhOptions.eval_mode of the timed runs: 0 library default (memo form from 28 objects, bit-identical to 3), "
                          "3 plain scan (every term from scratch), 1 delta evaluation, 2 memo form")
     ap.add_argument("--no-extras", action="store_true", help="skip the quick kernel-only rates of the other rooms")
     args = ap.parse_args()
@@ -424,7 +424,7 @@ def main():
         achieved = per_gpu_rate * f_live / 1e12
         scan_rate = quick_rate(k, room, args.chains, max(200, min(2000, args.iterations)), eval_mode=3, lanes_per_chain=args.lanes)
         roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                    "effective": args.eval_mode != 3 and n >= 32,
+                    "effective": args.eval_mode != 3 and n >= 28,
                     "effective_note": "algorithmic flops of a full evaluation x proposals/s: the default kernel returns the full evaluation's "
                                       "bits but executes a fraction of its arithmetic (exact memos); the plain scan, which executes all of it, "
                                       "is in full_scan",
@@ -434,7 +434,7 @@ def main():
                     "traffic_note": f"bytes per launch at 65536 chains from profiles/{PROFILE_FILE} (result block; independent of the iteration count)",
                     "flops_per_proposal": {"live": f_live, "contract": f_contract},
                     "achieved_contract": per_gpu_rate * f_contract / 1e12, "frac_contract": per_gpu_rate * f_contract / 1e12 / peak_tflops,
-                    "kernel": {0: "mh_delta_kernel<8, exact> (MH_EVAL_FULL in its memo form)" if n >= 32 else "mh_chain_kernel",
+                    "kernel": {0: "mh_delta_kernel<8, exact> (MH_EVAL_FULL in its memo form)" if n >= 28 else "mh_chain_kernel",
                                1: "mh_delta_kernel<., delta> (MH_EVAL_DELTA)", 2: "mh_delta_kernel<., exact> (MH_EVAL_MEMO)",
                                3: "mh_chain_kernel (MH_EVAL_FULL_SCAN)"}[args.eval_mode],
                     "kernel_ms_per_launch": kernel_max * 1e3 / args.steps,

@@ -29,7 +29,7 @@
 #endif
 
 #define MH_TLS __thread
-#define MH_MEMO_MIN_OBJS 32 /* nObjs from which MH_EVAL_FULL runs in its bit-identical memo form (measured: -7 % at 24, +17 % at 32, +27 % at 50, 1.9x at 100, 2.7x at 200) */
+#define MH_MEMO_MIN_OBJS 28 /* nObjs from which MH_EVAL_FULL runs in its bit-identical memo form (measured: -7 % at 24, -2 % at 26, +10 % at 28, +19 % at 32, +27 % at 50, 2.2x at 100, 3.4x at 200) */
 #define MH_MAX_BLOCKS_PER_SM 5 /* 128-thread blocks at the chain kernel's register cap (MH_MIN_BLOCKS in mh_kernels.cu) */
 
 static MH_TLS char g_err[512];

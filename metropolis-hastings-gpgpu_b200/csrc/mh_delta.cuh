@@ -497,7 +497,7 @@ __device__ __forceinline__ void delta_commit(const SmemProblem &P, const WarpSta
 // is taken from a's list only), dealt round-robin to the lanes of the group, and overwrites their entries;
 // then every lane adds ITS relationships r = g, g+G, ... from the memo -- the values and the order of
 // eval_terms' relationship loop, hence the same bits.  A rejected proposal puts the old entries back.
-// (The same memo inside the plain scan kernel, for rooms below 32 objects, was measured slower than evaluating
+// (The same memo inside the plain scan kernel, for rooms below 28 objects, was measured slower than evaluating
 // all R relationships: 1.7e9 against 2.4e9 proposals/s at n = 16 -- with 16 chains per warp the warp pays
 // for the chain with most touched relationships, and the kernel started to spill.)
 struct RelMemoStash {

@@ -592,8 +592,8 @@ def test_memo_mode_is_bit_identical_to_full_scan(kernel, cid, lanes, chains, ite
 
 
 def test_default_mode_switches_to_the_memo_transparently(kernel):
-    """MH_EVAL_FULL uses the memo form from 32 objects up; callers must not be able to tell."""
-    for n, C, R, lanes in ((70, 30, 40, 8), (33, 16, 20, 4), (120, 60, 90, 32)):
+    """MH_EVAL_FULL uses the memo form from 28 objects up; callers must not be able to tell."""
+    for n, C, R, lanes in ((70, 30, 40, 8), (33, 16, 20, 4), (28, 14, 20, 4), (120, 60, 90, 32)):
         room = S.make_room(n, C, R, 10.0, 8.0, 99)
         pa, ca = kernel.wrapper_ex(room, 48, 150, seed=3, lanes_per_chain=lanes, eval_mode=0)
         pb, cb = kernel.wrapper_ex(room, 48, 150, seed=3, lanes_per_chain=lanes, eval_mode=3)
@@ -601,7 +601,7 @@ def test_default_mode_switches_to_the_memo_transparently(kernel):
 
 
 def test_small_rooms_default_and_memo_equal_the_plain_scan(kernel):
-    """Below 32 objects MH_EVAL_FULL runs the plain scan (a relationship memo inside the scan kernel was
+    """Below 28 objects MH_EVAL_FULL runs the plain scan (a relationship memo inside the scan kernel was
     tried and lost: with 16 chains per warp some chain always has many touched relationships); whatever it
     runs, and the memo form when asked for, must return the plain scan's traces, layouts and costs for
     every lane width, with relationship hubs (more touched relationships than stash slots), frozen
