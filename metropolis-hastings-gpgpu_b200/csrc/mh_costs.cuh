@@ -29,6 +29,22 @@
 #define MH_SYM_UNROLL 8
 #endif
 
+// compute-sanitizer is not available on the development pool: a build with -DMH_DEBUG_BOUNDS checks every
+// index that comes from data (Philox draws, adjacency lists, memo columns) and every memo accessor, and
+// traps on a violation; tools/build_variant.sh dbg -DMH_DEBUG_BOUNDS + MH_LIB run the GPU tests against it.
+#ifdef MH_DEBUG_BOUNDS
+#include <stdio.h>
+#define MH_CHECK(cond)                                                                          \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            printf("MH_CHECK failed: %s at %s:%d (block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+            __trap();                                                                           \
+        }                                                                                       \
+    } while (0)
+#else
+#define MH_CHECK(cond) ((void)0)
+#endif
+
 namespace mh {
 
 constexpr int kSymUnroll = MH_SYM_UNROLL; // columns per trip of the symmetry loop
@@ -258,6 +274,7 @@ __device__ __noinline__ float2 rel_pen_impl(const int4 *rel_idx, const float4 *r
     const int4 id = rel_idx[r];       // distance pair (x, y) from rss[r], angle pair (z, w) from rsa[r]
     const float4 rg = rel_rng[r];     // 1/start, end, angleMin, angleMax
     const float4 ax = rel_aux[r];     // start, 1/norm, wraps
+    MH_CHECK(r >= 0 && id.x >= 0 && id.y >= 0 && id.z >= 0 && id.w >= 0);
     const float4 ps = Pc[id.x * CPW], pt = Pc[id.y * CPW];
     pd = 0.f;
     pa = 0.f;

@@ -54,7 +54,7 @@ template <int G> struct DeltaState {
     float2 *PR; // [R][CPW]    {distance penalty, angle penalty} of every relationship
     float *SV;  // [n + C][CPW] exact modes: area outside the room of object i's rectangle, then of clearance k's
     float *CR;  // [2][n][CPW] kModeExactCR: clearance row sums (object i's rectangle against every clearance)
-    int n;
+    int n, nC, nR;
     __host__ __device__ static int words(int n, int C, int R, int mode)
     {
         const int w = CPW * (4 * n + 2 * R + (mode != kModeDelta ? n + C : 0) + (mode == kModeExactCR ? 2 * n : 0));
@@ -63,15 +63,33 @@ template <int G> struct DeltaState {
     __device__ __forceinline__ void bind(float *base, int n_, int C, int R)
     {
         n = n_;
+        nC = C;
+        nR = R;
         KM = reinterpret_cast<float2 *>(base);
         PR = KM + 2 * n * CPW;
         SV = reinterpret_cast<float *>(PR + R * CPW);
         CR = SV + (n + C) * CPW;
     }
-    __device__ __forceinline__ float2 &km(int sel, int i, int c) const { return KM[(sel * n + i) * CPW + c]; }
-    __device__ __forceinline__ float2 &pr(int r, int c) const { return PR[r * CPW + c]; }
-    __device__ __forceinline__ float &sv(int i, int c) const { return SV[i * CPW + c]; }
-    __device__ __forceinline__ float &cr(int sel, int i, int c) const { return CR[(sel * n + i) * CPW + c]; }
+    __device__ __forceinline__ float2 &km(int sel, int i, int c) const
+    {
+        MH_CHECK((sel == 0 || sel == 1) && i >= 0 && i < n && c >= 0 && c < CPW);
+        return KM[(sel * n + i) * CPW + c];
+    }
+    __device__ __forceinline__ float2 &pr(int r, int c) const
+    {
+        MH_CHECK(r >= 0 && r < nR && c >= 0 && c < CPW);
+        return PR[r * CPW + c];
+    }
+    __device__ __forceinline__ float &sv(int i, int c) const
+    {
+        MH_CHECK(i >= 0 && i < n + nC && c >= 0 && c < CPW);
+        return SV[i * CPW + c];
+    }
+    __device__ __forceinline__ float &cr(int sel, int i, int c) const
+    {
+        MH_CHECK((sel == 0 || sel == 1) && i >= 0 && i < n && c >= 0 && c < CPW);
+        return CR[(sel * n + i) * CPW + c];
+    }
 };
 
 // Committed running sums of the additive terms (positive magnitudes, as in RawTerms).
@@ -221,6 +239,7 @@ __device__ __forceinline__ float sym_rescan_sum(const SmemProblem &P, const Warp
     if (mvb) row1 = b;
     for (;;) {
         const bool v0 = row0 != NONE, v1 = row1 != NONE;
+        MH_CHECK((!v0 || (row0 >= 0 && row0 < n)) && (!v1 || (row1 >= 0 && row1 < n)));
         const RowRef r0 = sym_row(h, Pc[(v0 ? row0 : a) * CPW]);
         const RowRef r1 = sym_row(h, Pc[(v1 ? row1 : a) * CPW]);
         float k0 = 5.0f, k1 = 5.0f;
@@ -308,6 +327,7 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
     const bool mvb = b >= 0;
     const bool any_b = __any_sync(FULL, mvb);
     const float pi_f = 0.5f * h->two_pi;
+    MH_CHECK(a >= 0 && a < n && b >= -1 && b < n && b != a && (sel == 0 || sel == 1));
 
     float d_pw = 0.f, d_pa = 0.f, d_vbx = 0.f, d_vby = 0.f, d_focal = 0.f, d_clr = 0.f, d_surf = 0.f;
 
@@ -533,6 +553,7 @@ __device__ __forceinline__ void rel_memo_eval(const SmemProblem &P, const float4
                 const int4 id = P.rel_idx[r];
                 if (id.x == a || id.y == a || id.z == a || id.w == a) r = -1;
             }
+            MH_CHECK(r < R && (R > 0 || tmax == 0));
             float pd, pe;
             rel_pen<CPW>(P, Pc, r >= 0 ? r : 0, pd, pe);
             if (r >= 0) {
@@ -622,6 +643,7 @@ __device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpStat
     const bool any_b = __any_sync(FULL, mvb);
     const float pi_f = 0.5f * h->two_pi;
     RawTerms t;
+    MH_CHECK(a >= 0 && a < n && b >= -1 && b < n && b != a && (sel == 0 || sel == 1));
 
     // ---- clearance, step 1 (S.CB still holds the CURRENT layout's rectangles): which rows must be
     //      re-added?  The moved objects' own rows, and every row whose overlap with a clearance sourced at
@@ -639,6 +661,7 @@ __device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpStat
             if (t0 < tot) {
                 const bool fa = t0 < na_c;
                 const int k = P.clr_adj[fa ? ca0 + t0 : cb0 + t0 - na_c];
+                MH_CHECK(k >= 0 && k < C);
                 const float4 pm = fa ? na : nb;
                 mo = CBc[k * CPW];
                 mn = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);

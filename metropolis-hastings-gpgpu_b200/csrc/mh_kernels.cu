@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
                 if (P.obj_frozen[a]) a = random_int(uniform01(rw.x), n - 1);
                 if (b >= 0 && P.obj_frozen[b]) b = random_int(uniform01(rw.y), n - 1);
             }
+            MH_CHECK(a >= 0 && a < n && b >= -1 && b < n);
             oa = S.P4[WS::at(a, c)];
             na = oa;
             if (p == 0) {                                      // translate, sigma = W/16, H/16 (Q19), snap to the room
@@ -407,6 +408,7 @@ __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
             }
         }
         const bool moved = a >= 0;
+        MH_CHECK(a >= -1 && a < n && b >= -1 && b < n && (b < 0 || a >= 0));
         const int a_e = moved ? a : 0;                           // no move: "move" object 0 onto itself (all deltas are 0)
         const float4 oa = S.P4[WS::at(a_e, c)];
         const float4 ob = S.P4[WS::at(b >= 0 ? b : a_e, c)];
