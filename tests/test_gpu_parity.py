@@ -762,6 +762,17 @@ def test_plain_c_caller_gets_the_same_bits(kernel, tmp_path, monkeypatch):
     assert costs["totalCosts"].min() > 3921.0        # the sampler climbs from the fixture's 3921.14
 
 
+def test_runs_are_deterministic(kernel):
+    """The same call three times gives the same bytes, for every evaluation mode and at a size that fills the
+    machine (a shared-memory race between the lanes of a group would show up as run-to-run differences)."""
+    for cid, chains, iters in ((3, 16384, 300), (4, 2048, 80), (2, 16384, 300)):
+        room = S.make_config(cid)
+        for mode in (0, 1, 2, 3):
+            runs = [kernel.wrapper_ex(room, chains, iters, seed=99, eval_mode=mode, result_mode=mode % 2) for _ in range(3)]
+            for p, c in runs[1:]:
+                assert p.tobytes() == runs[0][0].tobytes() and c.tobytes() == runs[0][1].tobytes(), (cid, mode)
+
+
 def test_full_size_memo_equals_scan(kernel):
     """At BASELINE sizes: the default (memo form) and the plain scan return the same bytes for all 65536
     chains of config 3 after 3000 iterations, and for 8192 chains of config 4 after 300."""
