@@ -13,6 +13,15 @@
  *                         batch of layouts: the GPU cost oracle.
  *   RefTimedWrapper    -- KernelWrapper bracketed by CUDA events (whole call, on the device
  *                         clock), for the throughput baseline.
+ *   RefProposeGPU      -- the reference's own propose() (Kernel.cu:576-704) applied once to each of
+ *                         nLayouts layouts, one thread per layout with its own XORWOW state seeded
+ *                         exactly as initRNG does (Kernel.cu:152-160): the pin for move-type and
+ *                         object frequencies, the dx/dy/dRot distributions, the clamp to the room
+ *                         and the one-sided rotation wrap.
+ *   RefAcceptGPU       -- the reference's own Accept() (Kernel.cu:706-713) on arrays of
+ *                         (costStar, costCur): the pin for the acceptance rule.
+ *   RefInitRngMs       -- device time of the reference's initRNG launch alone (Kernel.cu:939-943), so
+ *                         that the throughput baseline can be quoted with and without it.
  */
 #ifdef REF_NO_DIVERGENT_BARRIER
 /* Variant libKernel_ref_nb.so.  The reference's Copy() ends in __syncthreads() (Kernel.cu:747)
@@ -97,4 +106,77 @@ result *RefTimedWrapper(relationshipStruct *rss, relationshipAngleStruct *rsa, p
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return r;
+}
+
+/* ---- propose() / Accept() probes: the reference's own device functions, one thread per item ---- */
+
+__global__ void refProposeKernel(positionAndRotation *layouts, int nLayouts, Surface *srf, vertex *surfaceRectangle,
+                                 curandState *states, unsigned int seed)
+{
+    unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (unsigned int)nLayouts) return;
+    curand_init(seed + tid, tid, 0, &states[tid]);                      /* initRNG, Kernel.cu:159 */
+    propose(srf, layouts + (size_t)tid * srf->nObjs, surfaceRectangle, states, tid);
+}
+
+__global__ void refAcceptKernel(const double *star, const double *cur, int *out, int nItems, curandState *states, unsigned int seed)
+{
+    unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (unsigned int)nItems) return;
+    curand_init(seed + tid, tid, 0, &states[tid]);
+    out[tid] = Accept(star[tid], cur[tid], states, tid) ? 1 : 0;
+}
+
+/* layouts[nLayouts * n] are mutated in place: each receives ONE proposal of the reference. */
+extern "C" __attribute__((visibility("default")))
+int RefProposeGPU(Surface *srf, positionAndRotation *layouts, int nLayouts, vertex *surfaceRectangle, unsigned int seed)
+{
+    const size_t count = (size_t)srf->nObjs * nLayouts;
+    Surface *dS = up(srf, 1);
+    positionAndRotation *dL = up(layouts, count);
+    vertex *dSr = up(surfaceRectangle, 4);
+    curandState *dR = nullptr;
+    cudaMalloc(&dR, sizeof(curandState) * (size_t)nLayouts);
+    refProposeKernel<<<(nLayouts + 63) / 64, 64>>>(dL, nLayouts, dS, dSr, dR, seed);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(layouts, dL, sizeof(positionAndRotation) * count, cudaMemcpyDeviceToHost);
+    cudaFree(dS); cudaFree(dL); cudaFree(dSr); cudaFree(dR);
+    return (int)e;
+}
+
+extern "C" __attribute__((visibility("default")))
+int RefAcceptGPU(const double *star, const double *cur, int nItems, unsigned int seed, int *out)
+{
+    double *dA = up(star, nItems), *dB = up(cur, nItems);
+    int *dO = nullptr;
+    curandState *dR = nullptr;
+    cudaMalloc(&dO, sizeof(int) * (size_t)nItems);
+    cudaMalloc(&dR, sizeof(curandState) * (size_t)nItems);
+    refAcceptKernel<<<(nItems + 63) / 64, 64>>>(dA, dB, dO, nItems, dR, seed);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, dO, sizeof(int) * (size_t)nItems, cudaMemcpyDeviceToHost);
+    cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dR);
+    return (int)e;
+}
+
+/* The reference's RNG set-up launch alone, at the shape KernelWrapper uses (Kernel.cu:939-943:
+ * gridxDim blocks of blockxDim threads, one 48-byte XORWOW state per thread). */
+extern "C" __attribute__((visibility("default")))
+int RefInitRngMs(int gridxDim, int blockxDim, float *ms)
+{
+    curandState *dR = nullptr;
+    cudaError_t e = cudaMalloc(&dR, sizeof(curandState) * (size_t)gridxDim * (size_t)blockxDim);
+    if (e != cudaSuccess) return (int)e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    initRNG<<<gridxDim, blockxDim>>>(dR, 12345u);
+    cudaEventRecord(e1);
+    e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess && ms) cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(dR);
+    return (int)e;
 }

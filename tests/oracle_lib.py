@@ -143,6 +143,9 @@ class RefGPU:
         self.lib = C.CDLL(ref_gpu_path())
         self.lib.RefTimedWrapper.restype = C.c_void_p
         self.lib.RefSetHeap.argtypes = [C.c_size_t]
+        self.lib.RefProposeGPU.argtypes = [_P, _P, C.c_int, _P, C.c_uint]
+        self.lib.RefAcceptGPU.argtypes = [_P, _P, C.c_int, C.c_uint, _P]
+        self.lib.RefInitRngMs.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float)]
 
     def set_heap(self, nbytes):
         return self.lib.RefSetHeap(nbytes)
@@ -155,6 +158,34 @@ class RefGPU:
         if rc != 0:
             raise RuntimeError(f"RefCostsGPU: cuda error {rc}")
         return out
+
+    def propose_gpu(self, room, layouts, seed):
+        """The reference's own propose() (Kernel.cu:576-704) applied once to every layout, one thread and
+        one XORWOW state (seeded like initRNG, Kernel.cu:159) per layout.  Returns the mutated copies."""
+        out = np.ascontiguousarray(layouts).copy()
+        assert out.dtype == mh.positionAndRotation
+        rc = self.lib.RefProposeGPU(_ptr(room.srf), _ptr(out), C.c_int(len(out) // room.n), _ptr(room.surfaceRectangle), C.c_uint(seed))
+        if rc != 0:
+            raise RuntimeError(f"RefProposeGPU: cuda error {rc}")
+        return out
+
+    def accept_gpu(self, star, cur, seed):
+        """The reference's own Accept() (Kernel.cu:706-713) on arrays of (costStar, costCur)."""
+        a = np.ascontiguousarray(star, np.float64)
+        b = np.ascontiguousarray(cur, np.float64)
+        out = np.zeros(len(a), np.int32)
+        rc = self.lib.RefAcceptGPU(_ptr(a), _ptr(b), C.c_int(len(a)), C.c_uint(seed), _ptr(out))
+        if rc != 0:
+            raise RuntimeError(f"RefAcceptGPU: cuda error {rc}")
+        return out
+
+    def init_rng_ms(self, grid, block):
+        """Device milliseconds of the reference's initRNG launch alone (Kernel.cu:939-943)."""
+        ms = C.c_float(0)
+        rc = self.lib.RefInitRngMs(C.c_int(grid), C.c_int(block), C.byref(ms))
+        if rc != 0:
+            raise RuntimeError(f"RefInitRngMs: cuda error {rc}")
+        return float(ms.value)
 
     def run(self, room, n_chains, iterations, block=64):
         """The reference's KernelWrapper, unmodified.  Returns (points[n_chains, n], device ms of
