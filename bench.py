@@ -5,8 +5,11 @@ headline metric, on the 50-object living room (config 3: n=50, C=25, R=50, 65536
 
   python bench.py --gpus N --steps K --warmup W            this repo's sm_100a path
   python bench.py --eval-mode 3 ...                         the same with the plain scan (every term from scratch)
+  python bench.py --scaling strong --gpus N ...             BASELINE config 4 as named: 262144 chains of 200 objects
+                                                            x 1000 iterations SHARDED over the N GPUs (strong scaling)
   python bench.py --impl reference ...                      the reference's own kernel, rebuilt for
-                                                            sm_100 from /root/reference (oracle/_ref)
+                                                            sm_100 from /root/reference (oracle/_ref); one GPU always
+                                                            (the reference has no multi-GPU path, Kernel.cu:951)
 
 One step = one pass of the hot path over the whole batch: every chain runs `iterations` MH steps
 from the caller's layout.  The library's default evaluation (MH_EVAL_FULL) runs, from 28 objects up, in
@@ -15,8 +18,15 @@ full re-evaluation's (tested), at a fraction of the work; the plain scan's rate 
 HBM (KernelCreate once, then KernelReset + KernelRun per step, CUDA events around the kernel);
 `e2e` is the same job through the reference-facing call KernelWrapperEx with host buffers (H2D of
 the room, the kernels, D2H of every layout and its costs, result assembly).  Prints ONE JSON line.
+
+Sub-records of the default line: `config4_strong` (config 4 as named, total chains fixed, sharded over the N
+GPUs: kernel-only and e2e rates, arg-best time, a hash of global chains 0..1023 that must be equal for every N),
+`c_abi_multi_gpu` (N > 1: the same jobs through ONE process and the C ABI's device list, mhOptions.devices),
+`config2_as_named` (N = 1: 16 objects, 1024 chains x 10000 iterations, beside the reference kernel on the same
+workload).
 """
 import argparse
+import hashlib
 import importlib
 import json
 import os
@@ -165,6 +175,7 @@ def reference_gpu(config_id, chains, iters, steps, warmup, timeout_s=300):
     if out.returncode != 0:
         raise RuntimeError("reference kernel failed: " + (out.stderr.strip().splitlines() or ["?"])[-1])
     r = json.loads(out.stdout.strip().splitlines()[-1])
+    reference_gpu.last = r
     return r["proposals_per_s"], chains * iters / r["dev_s"], r["wall_s"]
 
 
@@ -278,20 +289,29 @@ def run_tempering(args, pkg, k, room, rank, local_rank, world, device, dist):
 
 
 def run_reference_arm(args, room, rank):
+    """The reference's own implementation, on ONE GPU whatever --gpus says: Kernel.cu:951 launches on the current
+    device and nothing in the reference spreads a job over devices, so n_gpus is reported as 1 and the driver's
+    per-N ratio at N > 1 reads "N GPUs of this repo against the reference's single GPU"."""
     if rank != 0:
         return
-    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 mixed", "data": "synthetic"}
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "gpus_requested": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 mixed",
+            "data": "synthetic"}
     chains, iters = args.ref_chains, args.ref_iterations
     try:
         if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libKernel_ref_nb.so")):
             raise RuntimeError("oracle/_ref/libKernel_ref_nb.so not built")
         v_wall, v_dev, step_s = reference_gpu(args.config, chains, iters, args.steps, args.warmup)
+        r = reference_gpu.last
         line.update(value=v_wall, ms_per_step=step_s * 1e3,
-                    config={"workload": f"config 3 living room n=50 C=25 R=50, bounded sample {chains} chains x {iters} iterations per step",
-                            "implementation": "reference Kernel.cu:873 KernelWrapper rebuilt for sm_100 (blockxDim=64; its one divergent __syncthreads, which deadlocks on sm_70+, neutralised), whole call incl. its H2D/D2H and curand init"},
+                    config={"workload": f"config {args.config} ({room.name}) n={room.n} C={room.C} R={room.R}, bounded sample {chains} chains x {iters} iterations per step "
+                                        f"({chains} blocks of 64 threads = {chains / (148 * 32):.2f} waves of 32 resident blocks per SM on 148 SMs)",
+                            "implementation": "reference Kernel.cu:873 KernelWrapper rebuilt for sm_100 (blockxDim=64; its one divergent __syncthreads, which deadlocks on sm_70+, neutralised), whole call incl. its H2D/D2H and curand init",
+                            "multi_gpu": "none in the reference: one GPU at every --gpus"},
                     cpu_baseline={"value": v_wall, "unit": UNIT, "cores": 0, "kind": "reference",
                                   "sample": f"{chains} chains x {iters} iterations; the reference's path is a CUDA kernel, timed on the same B200 (device-event rate {v_dev:.4g}/s)"},
+                    device_rates={"whole_call_device_events": v_dev, "without_init_rng": r.get("proposals_per_s_dev_without_init_rng"),
+                                  "init_rng_ms": r.get("init_rng_ms"), "note": "device-event time of KernelWrapper, and the same minus the initRNG launch (Kernel.cu:939-943) measured alone at the same launch shape"},
                     e2e={"value": v_wall, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
         try:   # the other baseline of BASELINE.md section 2, beside it: the transcribed C loop on the host cores
             line["cpu_port_baseline"] = cpu_baseline(room, target_seconds=5.0)
@@ -300,9 +320,191 @@ def run_reference_arm(args, room, rank):
     except Exception as ex:  # no GPU build of the reference: its algorithm as transcribed C on the host cores
         cb = cpu_baseline(room, target_seconds=max(5.0, 4.0 * args.steps))
         cb["sample"] += f" (reference kernel unavailable: {ex})"
-        line.update(value=cb["value"], ms_per_step=None, config={"workload": "config 3 living room n=50 C=25 R=50, bounded sample", "implementation": "oracle port on host cores"},
+        line.update(value=cb["value"], ms_per_step=None, config={"workload": f"config {args.config} ({room.name}), bounded sample", "implementation": "oracle port on host cores"},
                     cpu_baseline=cb, e2e={"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
     print(json.dumps(line), flush=True)
+
+
+class Plumbing:
+    """rank / world / device / collectives of one bench process."""
+
+    def __init__(self, torch, dist, rank, local_rank, world, device):
+        self.torch, self.dist, self.rank, self.local_rank, self.world, self.device = torch, dist, rank, local_rank, world, device
+        self.cpu_group = None
+        if world > 1:
+            try:   # a CPU-side group: ranks wait on it while rank 0 drives every GPU in-process (an NCCL barrier would spin on those GPUs)
+                self.cpu_group = dist.new_group(backend="gloo")
+            except Exception:
+                self.cpu_group = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def cpu_barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            if self.cpu_group is not None:
+                self.dist.barrier(group=self.cpu_group)
+            else:
+                self.dist.barrier()
+
+    def gmax(self, *values):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+
+def measure_job(pl, k, pkg, room, per_rank_chains, total_chains, offset, iterations, steps, warmup, flush, lanes=0, eval_mode=0, seed=20261018,
+                hash_chains=0, clock_gpu=None):
+    """One workload, sharded by global chain id: `value` leg (resident, KernelReset + KernelRun + NCCL arg-best per
+    step, CUDA events around the chain kernels) and `e2e` leg (KernelWrapperEx with host buffers per step).
+    Returns a dict; times are the max over ranks."""
+    torch = pl.torch
+    n = room.n
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = k.create(room, per_rank_chains, seed=seed, chain_offset=offset, total_chains=total_chains, lanes_per_chain=lanes, eval_mode=eval_mode)
+    ctx.set_stream(stream)
+    shape = ctx.shape()
+
+    def step():
+        flush.zero_()
+        ctx.reset()
+        ctx.run(iterations)
+        return pkg.dist.global_best(k, ctx, n, offset, total_chains, pl.rank, pl.world, pl.device, pl.dist if pl.world > 1 else None)
+
+    for _ in range(warmup):
+        step()
+    pl.barrier()
+    ms0, l0 = ctx.stats()
+    sampler = ClockSampler(clock_gpu) if clock_gpu is not None else None
+    t0 = time.perf_counter()
+    best = None
+    for _ in range(steps):
+        best = step()
+    pl.barrier()
+    wall = time.perf_counter() - t0
+    ms1, l1 = ctx.stats()
+    clocks = sampler.stop() if sampler else None
+    # the arg-best alone: packed-key arg-max on the device, 8-byte MAX all-reduce, owner's layout broadcast
+    t0 = time.perf_counter()
+    for _ in range(5):
+        pkg.dist.global_best(k, ctx, n, offset, total_chains, pl.rank, pl.world, pl.device, pl.dist if pl.world > 1 else None)
+    torch.cuda.synchronize()
+    argbest_s = (time.perf_counter() - t0) / 5
+    ctx.close()
+
+    # ---- e2e: the reference-facing call with HOST buffers ------------------------------------------------------
+    opts = dict(chain_offset=offset, total_chains=total_chains, lanes_per_chain=lanes, eval_mode=eval_mode)
+    k.wrapper_ex(room, per_rank_chains, max(1, iterations // 100), seed=7, **opts)            # warm
+    digest = None
+    pl.barrier()
+    t0 = time.perf_counter()
+    for s in range(steps):
+        res, pts, costs = k.wrapper_ex_raw(room, per_rank_chains, iterations, seed=7 + s, **opts)
+        e2e_best = float(costs["totalCosts"].max())            # the caller reads the result in place ...
+        if s == 0 and hash_chains and pl.rank == 0:
+            m = min(hash_chains, per_rank_chains)
+            digest = hashlib.sha256(pts[:m].tobytes() + costs[:m].tobytes()).hexdigest()[:16]
+        k.free(res)                                            # ... and hands it back
+    pl.barrier()
+    e2e_wall = time.perf_counter() - t0
+    wall_max, kernel_max, e2e_max, argbest_max = pl.gmax(wall, (ms1 - ms0) * 1e-3, e2e_wall, argbest_s)
+    proposals = float(total_chains) * iterations * steps
+    in_bytes = sum(a.nbytes for a in (room.rss, room.rsa, room.cfg, room.clearances, room.offlimits, room.vertices,
+                                      room.surfaceRectangle, room.srf)) + 24
+    return {"value": proposals / wall_max, "kernel_only": proposals / kernel_max, "e2e": proposals / e2e_max, "ms_per_step": wall_max * 1e3 / steps,
+            "kernel_ms_per_launch": kernel_max * 1e3 / steps, "e2e_ms_per_step": e2e_max * 1e3 / steps, "argbest_ms": argbest_max * 1e3,
+            "launches": int(l1 - l0), "clocks": clocks, "best": best, "shape": shape, "h2d_bytes_per_step": in_bytes,
+            "d2h_bytes_per_step": per_rank_chains * n * 24 + per_rank_chains * 32, "hash": digest, "e2e_best": e2e_best}
+
+
+def config4_strong(pl, k, pkg, flush, steps, warmup, clock_gpu=None):
+    """BASELINE config 4 exactly as named: 262144 chains of the 200-object hall x 1000 iterations, the chains SHARDED
+    over the N GPUs (strong scaling), NCCL arg-best.  Rank 0 holds global chains 0..1023 at every N <= 8, so the hash
+    of their layouts and costs (e2e leg, fixed seed) is the 1-GPU vs N-GPU per-chain identity check (BASELINE section 5
+    gate 4) on real hardware -- with the DEFAULT lane width (mhOptions.total_chains)."""
+    total, iters = 262144, 1000
+    room = pkg.synth.make_config(4)
+    offset, count = pkg.dist.shard(total, pl.rank, pl.world)
+    m = measure_job(pl, k, pkg, room, count, total, offset, iters, steps, warmup, flush, hash_chains=1024, clock_gpu=clock_gpu)
+    out_total = total * room.n * 24 + total * 32
+    return {"workload": f"config 4 ({room.name}): n={room.n} C={room.C} R={room.R}, {total} chains x {iters} iterations sharded over {pl.world} GPU(s)",
+            "scaling": "strong", "chains_per_gpu": count, "steps": steps, "warmup": warmup, "value": m["value"], "kernel_only": m["kernel_only"],
+            "e2e": m["e2e"], "unit": UNIT, "ms_per_step": m["ms_per_step"], "kernel_ms_per_launch": m["kernel_ms_per_launch"],
+            "e2e_ms_per_step": m["e2e_ms_per_step"], "e2e_overhead_ms": m["e2e_ms_per_step"] - m["kernel_ms_per_launch"],
+            "d2h_bytes_per_step_per_gpu": m["d2h_bytes_per_step"], "d2h_bytes_per_step_total": out_total, "argbest_ms": m["argbest_ms"],
+            "hash_chains_0_1023": m["hash"], "lanes_per_chain": m["shape"]["lanes_per_chain"], "eval_form": m["shape"]["eval_form"],
+            "best": {"global_chain": int(m["best"][0]), "totalCosts": float(m["best"][1])}, "clocks": m["clocks"],
+            "e2e_limit": "what e2e adds to the kernel is e2e_overhead_ms: the D2H of this GPU's slice of the 1.26 GB result block into the caller's "
+                         "malloc'd (pageable) memory, pre-faulted while the kernel runs; every rank copies its own slice concurrently",
+            "_measure": m}
+
+
+def c_abi_multi_gpu(pl, k, pkg, steps):
+    """The jobs through ONE process and the C ABI's device list (mhOptions.devices): what the reference's caller, a
+    single C# process calling KernelWrapper, can actually use.  Run by rank 0 over all N GPUs while the other ranks
+    wait on a CPU-side barrier."""
+    out = {}
+    if pl.rank == 0:
+        devs = list(range(pl.world))
+        for name, cid, total, iters in (("config3_weak", 3, 65536 * pl.world, 10000), ("config4_strong", 4, 262144, 1000)):
+            room = pkg.synth.make_config(cid)
+            k.wrapper_ex(room, total, max(1, iters // 100), seed=7, devices=devs)                  # warm
+            t0 = time.perf_counter()
+            digest = None
+            for s in range(steps):
+                res, pts, costs = k.wrapper_ex_raw(room, total, iters, seed=7 + s, devices=devs)
+                best = float(costs["totalCosts"].max())
+                if s == 0:
+                    digest = hashlib.sha256(pts[:1024].tobytes() + costs[:1024].tobytes()).hexdigest()[:16]
+                k.free(res)
+            dt = time.perf_counter() - t0
+            out[name] = {"workload": f"config {cid}: {total} chains x {iters} iterations over devices {devs} in one process",
+                         "e2e": total * iters * steps / dt, "unit": UNIT, "e2e_ms_per_step": dt * 1e3 / steps, "steps": steps,
+                         "hash_chains_0_1023": digest, "best_totalCosts": best,
+                         "call": "KernelWrapperEx(..., mhOptions{n_devices, devices[]}): one context + stream per device, every device "
+                                 "copies its slice into the one malloc'd result block on a thread of its own"}
+    pl.cpu_barrier()
+    return out
+
+
+def config2_as_named(k, pkg):
+    """BASELINE config 2 exactly as named: the 16-object bedroom, 1024 chains x 10000 iterations on one B200 (an
+    under-filled machine: 1024 chains are 7 warps per SM at the default lane width), beside the reference kernel
+    rebuilt for sm_100 on the SAME workload."""
+    room = pkg.synth.make_config(2)
+    chains, iters = 1024, 10000
+    with k.create(room, chains, seed=1) as ctx:
+        ctx.run(iters // 10)
+        ctx.synchronize()
+        ms0, _ = ctx.stats()
+        ctx.reset()
+        ctx.run(iters)
+        ctx.synchronize()
+        ms1, _ = ctx.stats()
+        shape = ctx.shape()
+    k.wrapper_ex(room, chains, 10, seed=3)
+    t0 = time.perf_counter()
+    reps = 3
+    for s in range(reps):
+        res, pts, costs = k.wrapper_ex_raw(room, chains, iters, seed=3 + s)
+        k.free(res)
+    e2e = chains * iters * reps / (time.perf_counter() - t0)
+    out = {"workload": f"config 2 ({room.name}): n={room.n} C={room.C} R={room.R}, {chains} chains x {iters} iterations", "unit": UNIT,
+           "kernel_only": chains * iters / ((ms1 - ms0) * 1e-3), "e2e": e2e, "lanes_per_chain": shape["lanes_per_chain"]}
+    try:
+        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libKernel_ref_nb.so")):
+            v_wall, v_dev, _ = reference_gpu(2, chains, iters, 1, 1, timeout_s=120)
+            r = reference_gpu.last
+            out["ref_gpu_baseline"] = {"value": v_wall, "unit": UNIT, "device_events": v_dev, "without_init_rng": r.get("proposals_per_s_dev_without_init_rng"),
+                                       "kind": "reference kernel rebuilt for sm_100 (divergent barrier neutralised), blockxDim=64, same GPU, same workload"}
+            out["e2e_over_reference"] = e2e / v_wall
+    except Exception as ex:
+        out["ref_gpu_baseline"] = {"unavailable": str(ex)}
+    return out
 
 
 def main():
@@ -312,9 +514,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=3)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --chains chains per GPU of --config (the headline); strong: BASELINE config 4 as named, 262144 chains sharded over the GPUs")
     ap.add_argument("--chains", type=int, default=65536, help="chains per GPU (weak scaling)")
     ap.add_argument("--iterations", type=int, default=10000)
-    ap.add_argument("--ref-chains", type=int, default=4096)
+    ap.add_argument("--ref-chains", type=int, default=8192, help="reference arm: 8192 blocks of 64 threads = 1.7 waves of 32 resident blocks per SM")
     ap.add_argument("--ref-iterations", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
@@ -322,7 +526,8 @@ def main():
     ap.add_argument("--eval-mode", type=int, default=0, choices=[0, 1, 2, 3],
                     help="mhOptions.eval_mode of the timed runs: 0 library default (memo form from 28 objects, bit-identical to 3), "
                          "3 plain scan (every term from scratch), 1 delta evaluation, 2 memo form")
-    ap.add_argument("--no-extras", action="store_true", help="skip the quick kernel-only rates of the other rooms")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (other rooms, config 4 strong, config 2 as named, in-process multi-GPU)")
+    ap.add_argument("--sub-steps", type=int, default=2, help="timed steps of the sub-records (config 4 strong, in-process multi-GPU)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -346,6 +551,7 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    pl = Plumbing(torch, dist, rank, local_rank, world, device)
     k = pkg.Kernel()
     info = k.device_info()
     if tempering:
@@ -354,66 +560,52 @@ def main():
             dist.barrier()
             dist.destroy_process_group()
         return
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
+
+    if args.scaling == "strong":
+        c4 = config4_strong(pl, k, pkg, flush, args.steps, args.warmup, clock_gpu=local_rank if rank == 0 else None)
+        if rank == 0:
+            m = c4.pop("_measure")
+            room4 = pkg.synth.make_config(4)
+            peaks = measured_peaks()
+            sm_max_mhz = float(peaks.get("sm_max_mhz") or info["sm_clock_khz"] / 1e3)
+            peak_tflops = info["sm_count"] * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+            per_gpu = m["kernel_only"] / world
+            f_live = room4.flops_per_proposal(live=True)
+            line = {"metric": "MH proposals evaluated/sec (chains x iters/s) at 200 objects, 262144 chains sharded", "value": m["value"], "unit": UNIT,
+                    "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": c4["workload"], "parallelism": f"262144 chains sharded over {world} GPU(s) by global chain id, NCCL arg-best",
+                               "l2": "256 MiB memset between steps; the chain state lives in shared memory"},
+                    "e2e": {"value": m["e2e"], "unit": UNIT, "h2d_bytes_per_step": m["h2d_bytes_per_step"], "d2h_bytes_per_step": m["d2h_bytes_per_step"],
+                            "call": "KernelWrapperEx per rank (host buffers in, malloc'd result block out)"},
+                    "gpu_launches": m["launches"], "clocks": m["clocks"], "device": info["name"],
+                    "roofline": {"bound": "fp32", "achieved": per_gpu * f_live / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
+                                 "frac": per_gpu * f_live / 1e12 / peak_tflops, "effective": True, "traffic": None,
+                                 "kernel": "mh_delta_kernel<32, exact + clearance row sums>", "kernel_ms_per_launch": m["kernel_ms_per_launch"]},
+                    "config4_strong": c4}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     n = room.n
     total_chains = args.chains * world
     offset = rank * args.chains
+    m = measure_job(pl, k, pkg, room, args.chains, total_chains, offset, args.iterations, args.steps, args.warmup, flush, lanes=args.lanes,
+                    eval_mode=args.eval_mode, clock_gpu=local_rank if rank == 0 else None)
+    value, e2e_value, clocks, best = m["value"], m["e2e"], m["clocks"], m["best"]
+    kernel_max = m["kernel_ms_per_launch"] * 1e-3 * args.steps
 
-    def barrier():
+    extras = {}
+    if not args.no_extras:
+        sub = max(1, min(args.sub_steps, args.steps))
+        c4 = config4_strong(pl, k, pkg, flush, sub, 1)
+        c4.pop("_measure", None)
+        extras["config4_strong"] = c4
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = k.create(room, args.chains, seed=20261018, chain_offset=offset, lanes_per_chain=args.lanes, eval_mode=args.eval_mode)
-    ctx.set_stream(stream)
-
-    def step():
-        flush.zero_()
-        ctx.reset()
-        ctx.run(args.iterations)
-        return pkg.dist.global_best(k, ctx, n, offset, total_chains, rank, world, device, dist if world > 1 else None)
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    ctx.stats()
-    ms0, l0 = ctx.stats()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    t0 = time.perf_counter()
-    best = None
-    for _ in range(args.steps):
-        best = step()
-    barrier()
-    wall = time.perf_counter() - t0
-    ms1, l1 = ctx.stats()
-    clocks = sampler.stop() if sampler else None
-    kernel_s = (ms1 - ms0) * 1e-3                       # CUDA events around the chain kernels only
-    t = torch.tensor([wall, kernel_s], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall_max, kernel_max = float(t[0]), float(t[1])
-    proposals = float(total_chains) * args.iterations * args.steps
-    value = proposals / wall_max
-
-    # ---- e2e: the reference-facing call with HOST buffers --------------------------------------
-    in_bytes = sum(a.nbytes for a in (room.rss, room.rsa, room.cfg, room.clearances, room.offlimits, room.vertices,
-                                      room.surfaceRectangle, room.srf)) + 24
-    out_bytes = args.chains * n * 24 + args.chains * 32
-    k.wrapper_ex(room, args.chains, max(1, args.iterations // 100), seed=7, chain_offset=offset, eval_mode=args.eval_mode)   # warm
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        res, pts, costs = k.wrapper_ex_raw(room, args.chains, args.iterations, seed=7 + s, chain_offset=offset, lanes_per_chain=args.lanes,
-                                           eval_mode=args.eval_mode)
-        e2e_best = float(costs["totalCosts"].max())        # the caller reads the result in place ...
-        k.free(res)                                        # ... and hands it back
-    barrier()
-    e2e_wall = time.perf_counter() - t0
-    t = torch.tensor([e2e_wall], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = proposals / float(t[0])
+            extras["c_abi_multi_gpu"] = c_abi_multi_gpu(pl, k, pkg, sub)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -434,7 +626,7 @@ def main():
                     "traffic_note": f"bytes per launch at 65536 chains from profiles/{PROFILE_FILE} (result block; independent of the iteration count)",
                     "flops_per_proposal": {"live": f_live, "contract": f_contract},
                     "achieved_contract": per_gpu_rate * f_contract / 1e12, "frac_contract": per_gpu_rate * f_contract / 1e12 / peak_tflops,
-                    "kernel": {0: "mh_delta_kernel<8, exact> (MH_EVAL_FULL in its memo form)" if n >= 28 else "mh_chain_kernel",
+                    "kernel": {0: f"mh_delta_kernel<{m['shape']['lanes_per_chain']}, exact> (MH_EVAL_FULL in its memo form)" if n >= 28 else "mh_chain_kernel",
                                1: "mh_delta_kernel<., delta> (MH_EVAL_DELTA)", 2: "mh_delta_kernel<., exact> (MH_EVAL_MEMO)",
                                3: "mh_chain_kernel (MH_EVAL_FULL_SCAN)"}[args.eval_mode],
                     "kernel_ms_per_launch": kernel_max * 1e3 / args.steps,
@@ -443,20 +635,22 @@ def main():
                                    "chain state lives in shared memory",
                     "frac_at_observed_clock": (achieved / (info["sm_count"] * 256 * clocks["sm_mhz"] * 1e6 / 1e12)) if clocks and clocks.get("sm_mhz") else None}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": wall_max * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"config {args.config} ({room.name}): n={n} C={room.C} R={room.R}, {args.chains} chains/GPU x {args.iterations} iterations, all cost terms, beta=2",
                            "evaluation": {0: "MH_EVAL_FULL (library default): every proposal's full cost, bit-identical to the plain re-evaluation, computed through exact memos",
                                           1: "MH_EVAL_DELTA: incremental running sums, statistically equivalent to the full evaluation",
                                           2: "MH_EVAL_MEMO: the full evaluation's bits through exact memos",
                                           3: "MH_EVAL_FULL_SCAN: every live cost term of every proposal from scratch"}[args.eval_mode],
-                           "chains_total": total_chains, "lanes_per_chain": args.lanes or "auto", "parallelism": f"chains sharded over {world} GPU(s), NCCL arg-best",
+                           "chains_total": total_chains, "lanes_per_chain": m["shape"]["lanes_per_chain"], "parallelism": f"chains sharded over {world} GPU(s), NCCL arg-best",
                            "l2": "256 MiB memset between steps; the chain state lives in shared memory"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m["h2d_bytes_per_step"], "d2h_bytes_per_step": m["d2h_bytes_per_step"],
                         "call": "KernelWrapperEx (host buffers in, malloc'd result block out)"},
-                "gpu_launches": int(l1 - l0), "roofline": roofline, "clocks": clocks,
+                "gpu_launches": m["launches"], "roofline": roofline, "clocks": clocks, "argbest_ms": m["argbest_ms"],
                 "best": {"global_chain": int(best[0]), "totalCosts": float(best[1])}, "device": info["name"]}
+        line.update(extras)
         if not args.no_extras and world == 1:                    # the side measurements run at N=1 only
+            line["config2_as_named"] = config2_as_named(k, pkg)
             line["other_configs_kernel_only"] = other_configs(k, pkg)
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_baseline(room)
@@ -478,12 +672,13 @@ def main():
             try:
                 if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libKernel_ref_nb.so")):
                     v_wall, v_dev, _ = reference_gpu(args.config, args.ref_chains, args.ref_iterations, 1, 1, timeout_s=120)
+                    r = reference_gpu.last
                     line["ref_gpu_baseline"] = {"value": v_wall, "unit": UNIT, "kind": "reference kernel rebuilt for sm_100 (divergent barrier neutralised), blockxDim=64, same GPU",
+                                                "device_events": v_dev, "without_init_rng": r.get("proposals_per_s_dev_without_init_rng"),
                                                 "sample": f"{args.ref_chains} chains x {args.ref_iterations} iterations, whole KernelWrapper call; device-event rate {v_dev:.4g}/s"}
             except Exception as ex:
                 line["ref_gpu_baseline"] = {"unavailable": str(ex)}
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

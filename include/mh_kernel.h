@@ -56,13 +56,27 @@ enum {
                          MH_EVAL_FULL, not bit-identical (csrc/mh_delta.cuh)                            */
 };
 
+/* mhOptions.flags */
+enum {
+    MH_OPT_EXPLICIT_DEVICE = 1u /* `device` names a CUDA ordinal even when it is 0.  Without this bit device <= 0
+                                   means the caller's CURRENT device, so that a zero-initialised struct behaves
+                                   like the reference, which never calls cudaSetDevice (Kernel.cu:873-984); a
+                                   positive `device` is an ordinal with or without the bit                   */
+};
+
+#define MH_MAX_DEVICES 8
+
 typedef struct mhOptions {
-    uint32_t struct_size;       /* = sizeof(mhOptions); lets the struct grow compatibly              */
-    uint32_t flags;             /* reserved, 0                                                       */
+    uint32_t struct_size;       /* = sizeof(mhOptions); lets the struct grow compatibly: a caller compiled
+                                   against an older, shorter struct keeps working (missing tail = zeros)  */
+    uint32_t flags;             /* MH_OPT_*                                                          */
     uint64_t seed;              /* Philox key.  KernelWrapper (no options) uses time(NULL) like the
                                    reference (Kernel.cu:943) unless env MH_SEED is set               */
     uint64_t chain_offset;      /* global id of this call's first chain: chain g = chain_offset + i
-                                   draws Philox stream g, so a sharded run equals the unsharded one  */
+                                   draws Philox stream g, so a sharded run equals the unsharded one
+                                   bit for bit -- provided every shard uses the same lane width (it
+                                   fixes the order of the float reductions): pass the job's size in
+                                   total_chains (below) or pin lanes_per_chain                       */
     uint64_t iteration_offset;  /* first iteration index (resume: continue the same Philox stream)   */
     double beta_start;          /* 0 -> 2.0                                                          */
     double beta_end;            /* 0 -> beta_start                                                   */
@@ -70,8 +84,9 @@ typedef struct mhOptions {
     int32_t schedule_length;    /* iterations over which the schedule runs; 0 -> this call's count   */
     int32_t result_mode;        /* MH_RESULT_*                                                       */
     int32_t eval_mode;          /* MH_EVAL_*                                                         */
-    int32_t lanes_per_chain;    /* 0 = choose from nObjs and chain count; else 1,2,4,8,16,32         */
-    int32_t device;             /* CUDA device ordinal; -1 = the caller's current device             */
+    int32_t lanes_per_chain;    /* 0 = choose from nObjs and the job's chain count; else 1,2,4,8,16,32 */
+    int32_t device;             /* <= 0: the caller's current device (0 with MH_OPT_EXPLICIT_DEVICE: GPU 0);
+                                   > 0: that CUDA ordinal.  Ignored when n_devices > 1                 */
     /* parallel tempering (extension; 0 rungs = off).  Chains are grouped in ladders of
      * `tempering_rungs` consecutive global chain ids; rung r starts at
      * beta_start * (beta_end/beta_start)^(r/(rungs-1)); every `exchange_interval`
@@ -83,7 +98,26 @@ typedef struct mhOptions {
      * g % ranks == r, so neighbouring rungs live on different GPUs and exchange through
      * KernelTemperingExchange (below). */
     uint64_t chain_stride;
+    /* ---- appended in round 2 (offset 88) ---- */
+    /* Chains of the WHOLE job of which this context is one shard (0 -> this context's own count).  The
+     * default lane width and evaluation form are chosen from it, never from the shard's own count, so
+     * that every shard of a job -- and the same job run unsharded -- use the same float reduction order
+     * and return the same bits without anybody pinning lanes_per_chain. */
+    uint64_t total_chains;
+    /* Multi-GPU inside ONE process, behind this C ABI (the reference's caller is a single C# process,
+     * Kernel.cu:873).  n_devices > 1: the chains [chain_offset, chain_offset + nChains) are split into
+     * contiguous ranges over devices[0 .. n_devices-1] (whole ladders when tempering), one context and one
+     * stream per device, all running concurrently; results are copied from every device straight into
+     * the caller's one result block; KernelBest / KernelTopK merge the per-device answers.  Per-chain
+     * results are bit-identical to the one-device run.  0 or 1: one device (`device`).  An ordinal may repeat
+ * (those shards then share that GPU; the tests use it to run this path on a one-GPU box).
+     * Env MH_DEVICES ("all" or a comma list) supplies the list when the options carry none -- the way to
+     * spread the reference's own entry point, KernelWrapper, over several GPUs. */
+    int32_t n_devices;
+    int32_t devices[MH_MAX_DEVICES];
+    int32_t reserved0;
 } mhOptions;
+MH_STATIC_ASSERT(sizeof(mhOptions) == 136, "mhOptions");
 
 /* One record per chain per iteration, for trajectory tests (KernelRunTraced). */
 typedef struct mhTraceEntry {
@@ -157,7 +191,11 @@ MH_API int KernelSynchronize(mhContext *ctx);
 /* Copy results to host buffers: points[nChains*n], costs[nChains] (either may be NULL). */
 MH_API int KernelResults(mhContext *ctx, point *points, resultCosts *costs);
 /* Device addresses of the result buffers (valid until KernelDestroy), for zero-copy
- * consumers such as a collective over the per-chain costs. */
+ * consumers such as a collective over the per-chain costs.  STREAM ORDERING: the buffers are written by
+ * work enqueued on the context's stream (a non-blocking stream of the library's own unless
+ * KernelSetStream named another).  A consumer on a different stream must first KernelSynchronize(ctx),
+ * or make the context run on its own stream with KernelSetStream.  Not available on a multi-device
+ * context (n_devices > 1): there is no single device address. */
 MH_API int KernelDeviceResults(mhContext *ctx, void **d_points, void **d_costs);
 /* Run on a caller-provided CUDA stream (a cudaStream_t passed as void*).  NULL = a stream of the
  * library's own; to name the legacy default stream pass cudaStreamLegacy, i.e. (void*)0x1. */
@@ -181,7 +219,12 @@ MH_API int KernelTopKDistinct(mhContext *ctx, int k, float minDistance, float ro
 /* Multi-GPU arg-best: writes to the DEVICE address d_key one signed 64-bit key that orders like
  * (totalCosts of this context's best chain, lower global chain id first).  A MAX all-reduce of
  * the keys over all ranks (NCCL has no arg-max) yields the global best; KernelDecodeBestKey
- * recovers the global chain id and its totalCosts.  Asynchronous on the context's stream. */
+ * recovers the global chain id and its totalCosts.  The key keeps the low 32 bits of the global id:
+ * the call fails if this context holds a chain with a global id >= 2^32.
+ * STREAM ORDERING: asynchronous on the context's stream -- d_key is valid for work enqueued LATER ON
+ * THAT STREAM; a collective on another stream (torch's, NCCL's) must be ordered after it with
+ * KernelSynchronize(ctx) or by running the context on that stream (KernelSetStream).  The same holds for
+ * the arrays of KernelTemperingState. */
 MH_API int KernelBestKey(mhContext *ctx, void *d_key);
 MH_API void KernelDecodeBestKey(long long key, unsigned long long *globalChain, float *total);
 /* Restart every chain from the caller's layout (iteration counter back to 0). */
@@ -203,7 +246,8 @@ MH_API int KernelTemperingExchange(mhContext *ctx, const void *d_all_totals, con
  * rungs-1 or -1. */
 MH_API int KernelTemperingStats(mhContext *ctx, long long *attempts, long long *accepted);
 /* Milliseconds the device spent in the MH kernels since creation (CUDA events) and how many
- * kernels were launched. */
+ * kernels were launched.  Multi-device context: the devices run concurrently, kernel_ms is the largest
+ * per-device sum and launches the total over the devices. */
 MH_API int KernelStats(mhContext *ctx, double *kernel_ms, long long *launches);
 MH_API void KernelDestroy(mhContext *ctx);
 
@@ -211,6 +255,15 @@ MH_API void KernelDestroy(mhContext *ctx);
  * and frees 12 buffers per call, Kernel.cu:879-967).  KernelTrim returns the cached blocks of
  * the current device to the driver. */
 MH_API int KernelTrim(void);
+
+/* How the context was laid out: lanes per chain of the chain kernel (the lane width fixes the float
+ * reduction order: contexts compare bit for bit only at equal width), the evaluation form actually run
+ * (MH_EVAL_FULL_SCAN, MH_EVAL_MEMO or MH_EVAL_DELTA), the number of devices, and each device's ordinal and
+ * chain count (arrays of MH_MAX_DEVICES entries; any pointer may be NULL).  Returns 0 or -1. */
+MH_API int KernelShape(mhContext *ctx, int *lanesPerChain, int *evalForm, int *nDevices, int *deviceOrdinals, int *chainsPerDevice);
+
+/* Number of CUDA devices visible to the process (-1 on error). */
+MH_API int KernelDeviceCount(void);
 
 /* Library / device facts for harnesses: returns 0 and fills what is non-NULL. */
 MH_API int KernelDeviceInfo(int *smCount, int *smClockKHz, int *ccMajor, int *ccMinor,

@@ -17,7 +17,9 @@ _P = C.c_void_p
 
 EXPORTS = ("KernelWrapper", "KernelWrapperEx", "KernelFree", "KernelLastError", "KernelEvalCosts", "KernelCreate", "KernelRun",
            "KernelRunTraced", "KernelSynchronize", "KernelResults", "KernelDeviceResults", "KernelSetStream", "KernelBest",
-           "KernelStats", "KernelDestroy", "KernelDeviceInfo", "KernelBestKey", "KernelDecodeBestKey", "KernelReset", "KernelTrim", "KernelTemperingState", "KernelTemperingExchange", "KernelTopK", "KernelTopKDistinct", "KernelTemperingStats")
+           "KernelStats", "KernelDestroy", "KernelDeviceInfo", "KernelBestKey", "KernelDecodeBestKey", "KernelReset", "KernelTrim",
+           "KernelTemperingState", "KernelTemperingExchange", "KernelTopK", "KernelTopKDistinct", "KernelTemperingStats", "KernelShape",
+           "KernelDeviceCount")
 
 
 class KernelError(RuntimeError):
@@ -37,11 +39,26 @@ def _ptr(a):
 
 
 def make_options(**kw):
+    """mhOptions from keyword arguments.  `device=k` names CUDA ordinal k (also 0: the explicit-device flag is
+    set); `devices=[...]` (or an int N = the first N ordinals) spreads the chains over several GPUs in-process."""
     o = np.zeros(1, L.mhOptions)
     o["struct_size"] = L.mhOptions.itemsize
     o["device"] = -1
     for k, v in kw.items():
-        o[k] = v
+        if k == "devices":
+            if v is None:
+                continue
+            ids = list(range(v)) if isinstance(v, int) else list(v)
+            if len(ids) > L.MH_MAX_DEVICES:
+                raise KernelError(f"at most {L.MH_MAX_DEVICES} devices")
+            o["n_devices"] = len(ids)
+            o["devices"][0, :len(ids)] = ids
+        elif k == "device":
+            o["device"] = v
+            if v is not None and v >= 0:
+                o["flags"] |= L.MH_OPT_EXPLICIT_DEVICE
+        else:
+            o[k] = v
     return o
 
 
@@ -56,26 +73,44 @@ class Kernel:
             if not os.path.exists(path):
                 raise KernelError(f"{path} is missing: build it with `make -C {_HERE}/csrc` (or __graft_entry__.build())")
             lib = C.CDLL(path)
-            lib.KernelWrapper.restype = _P
-            lib.KernelWrapperEx.restype = _P
-            lib.KernelCreate.restype = _P
-            lib.KernelLastError.restype = C.c_char_p
-            lib.KernelFree.argtypes = [_P]
-            lib.KernelDestroy.argtypes = [_P]
-            lib.KernelRun.argtypes = [_P, C.c_int]
-            lib.KernelRunTraced.argtypes = [_P, C.c_int, _P]
-            lib.KernelSynchronize.argtypes = [_P]
-            lib.KernelResults.argtypes = [_P, _P, _P]
-            lib.KernelSetStream.argtypes = [_P, _P]
-            lib.KernelBestKey.argtypes = [_P, _P]
-            lib.KernelReset.argtypes = [_P]
-            lib.KernelTopK.argtypes = [_P, C.c_int, _P, _P]
-            lib.KernelTopKDistinct.argtypes = [_P, C.c_int, C.c_float, C.c_float, _P, _P]
-            lib.KernelTemperingState.argtypes = [_P, C.POINTER(_P), C.POINTER(_P)]
-            lib.KernelTemperingExchange.argtypes = [_P, _P, _P]
-            lib.KernelTemperingStats.argtypes = [_P, _P, _P]
-            lib.KernelDecodeBestKey.argtypes = [C.c_longlong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]
-            lib.KernelDecodeBestKey.restype = None
+            I, F, D, LL = C.c_int, C.c_float, C.c_double, C.c_longlong
+            PI_, PF = C.POINTER(C.c_int), C.POINTER(C.c_float)
+            room8 = [_P] * 8                                    # rss, rsa, cfg, clearances, offlimits, vertices, surfaceRectangle, srf
+            # (restype, argtypes) of EVERY export: a handle is a 64-bit pointer, and ctypes would pass a bare
+            # Python int as a 32-bit C int (truncating any context allocated above 4 GiB) without this table
+            sig = {
+                "KernelWrapper": (_P, room8 + [_P]),
+                "KernelWrapperEx": (_P, room8 + [_P, _P]),
+                "KernelFree": (None, [_P]),
+                "KernelLastError": (C.c_char_p, []),
+                "KernelEvalCosts": (I, [_P, _P, _P, I, _P, _P, _P, _P, _P, _P]),
+                "KernelCreate": (_P, room8 + [I, _P]),
+                "KernelRun": (I, [_P, I]),
+                "KernelRunTraced": (I, [_P, I, _P]),
+                "KernelSynchronize": (I, [_P]),
+                "KernelResults": (I, [_P, _P, _P]),
+                "KernelDeviceResults": (I, [_P, C.POINTER(_P), C.POINTER(_P)]),
+                "KernelSetStream": (I, [_P, _P]),
+                "KernelBest": (I, [_P, PI_, PF]),
+                "KernelStats": (I, [_P, C.POINTER(D), C.POINTER(LL)]),
+                "KernelDestroy": (None, [_P]),
+                "KernelDeviceInfo": (I, [PI_, PI_, PI_, PI_, C.c_char_p, I]),
+                "KernelBestKey": (I, [_P, _P]),
+                "KernelDecodeBestKey": (None, [LL, C.POINTER(C.c_ulonglong), PF]),
+                "KernelReset": (I, [_P]),
+                "KernelTrim": (I, []),
+                "KernelTemperingState": (I, [_P, C.POINTER(_P), C.POINTER(_P)]),
+                "KernelTemperingExchange": (I, [_P, _P, _P]),
+                "KernelTopK": (I, [_P, I, _P, _P]),
+                "KernelTopKDistinct": (I, [_P, I, F, F, _P, _P]),
+                "KernelTemperingStats": (I, [_P, _P, _P]),
+                "KernelShape": (I, [_P, PI_, PI_, PI_, _P, _P]),
+                "KernelDeviceCount": (I, []),
+            }
+            assert set(sig) == set(EXPORTS)
+            for name, (res, args) in sig.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
             Kernel._lib = lib
         self.lib = Kernel._lib
 
@@ -168,6 +203,12 @@ class Kernel:
         self.lib.KernelDecodeBestKey(C.c_longlong(int(key)), C.byref(g), C.byref(t))
         return g.value, t.value
 
+    def device_count(self):
+        n = self.lib.KernelDeviceCount()
+        if n < 0:
+            self._fail("KernelDeviceCount")
+        return n
+
     def create(self, room, n_chains, **opts):
         return Context(self, room, n_chains, **opts)
 
@@ -217,6 +258,7 @@ class Context:
             stream_handle = 1
         if self.k.lib.KernelSetStream(self.h, _P(stream_handle)) != 0:
             self.k._fail("KernelSetStream")
+        self._stream_handle = stream_handle if stream_handle != 1 else 0
 
     def best(self):
         i, t = C.c_int(), C.c_float()
@@ -267,6 +309,16 @@ class Context:
         if m < 0:
             self.k._fail("KernelTopKDistinct")
         return idx[:m], tot[:m]
+
+    def shape(self):
+        """How the context was laid out: lanes per chain, evaluation form, and (device, chains) per device."""
+        lanes, form, nd = C.c_int(), C.c_int(), C.c_int()
+        dev = np.zeros(L.MH_MAX_DEVICES, np.int32)
+        cnt = np.zeros(L.MH_MAX_DEVICES, np.int32)
+        if self.k.lib.KernelShape(self.h, C.byref(lanes), C.byref(form), C.byref(nd), _ptr(dev), _ptr(cnt)) != 0:
+            self.k._fail("KernelShape")
+        return {"lanes_per_chain": lanes.value, "eval_form": form.value, "devices": [int(d) for d in dev[:nd.value]],
+                "chains_per_device": [int(c) for c in cnt[:nd.value]]}
 
     def stats(self):
         ms, n = C.c_double(), C.c_longlong()

@@ -23,6 +23,7 @@
 #include "../../include/mh_kernel.h"
 #include "mh_abi.h"
 
+#include <pthread.h>
 #if defined(__linux__)
 #include <sys/mman.h>
 #include <unistd.h>
@@ -273,6 +274,11 @@ static int pack_problem(const relationshipStruct *rss, const relationshipAngleSt
 typedef struct evPair { void *e0, *e1; } evPair;
 
 struct mhContext {
+    /* multi-device parent (mhOptions.n_devices > 1): owns one ordinary context per device and no device memory of
+     * its own; shard s holds the chains [shard_first[s], shard_first[s] + shards[s]->n_chains) of this context */
+    int n_shards;
+    struct mhContext **shards;
+    int *shard_first;
     int device;        /* device the context lives on */
     int n, C, R, n_chains, lanes, score_lanes, delta_warps;
     int eval_internal; /* what the chain kernel runs: 0 full scan, 1 delta, 2 exact symmetry memo */
@@ -282,6 +288,7 @@ struct mhContext {
     float *d_x, *d_y, *d_rot, *d_cur, *d_best, *d_beta, *d_beta_snap;
     uint16_t *d_perm;
     void *d_points, *d_costs, *d_scratch, *d_exch_stats;
+    void *h_scratch;   /* 64 bytes of pinned host memory: small read-backs that must not block the host */
     void *stream;
     int own_stream;
     uint64_t it_done;  /* iterations already run (relative to opt.iteration_offset) */
@@ -289,6 +296,14 @@ struct mhContext {
     evPair *ev; int n_ev, cap_ev;
     double kernel_ms; long long launches;
 };
+
+/* mhOptions.device -> CUDA ordinal or -1 = the caller's current device (include/mh_kernel.h) */
+static int resolve_device(const mhOptions *o)
+{
+    if (o->device > 0) return o->device;
+    if (o->device == 0 && (o->flags & MH_OPT_EXPLICIT_DEVICE)) return 0;
+    return -1;
+}
 
 static int enter_device(int want, int *prev)
 {
@@ -361,7 +376,7 @@ static int choose_lanes(int n, int C, int R, int smem_words, int n_chains, int r
  * (measured on B200: n=8 -> 1, n=16 -> 2, n=50 -> 8, n=200 -> 32 lanes).  Few chains: widen the groups
  * until the machine is covered.  Blocks of 8 warps when shared memory allows and the grid still covers
  * the SMs (the problem blob is staged once per block: 8 >= 4 at n = 50, +20 % at n = 200). */
-static int choose_delta_shape(int n, int C, int R, int smem_words, int n_chains, int requested, int eval_mode, int *lanes_out, int *warps_out)
+static int choose_delta_shape(int n, int C, int R, int smem_words, int job_chains, int n_chains, int requested, int eval_mode, int *lanes_out, int *warps_out)
 {
     int max_block = 0, max_sm = 0, sms = 0;
     int e = mhdev_device_limits(&max_block, &max_sm, &sms, NULL, NULL, NULL, NULL, 0);
@@ -370,7 +385,7 @@ static int choose_delta_shape(int n, int C, int R, int smem_words, int n_chains,
     if (requested <= 0 && env) requested = atoi(env);
     int G = 1;
     while (G < 32 && G * 8 < n) G *= 2;
-    while (G < 32 && (double)n_chains * G / 32.0 < 8.0 * sms) G *= 2;      /* under-filled machine: wider groups */
+    while (G < 32 && (double)job_chains * G / 32.0 < 8.0 * sms) G *= 2;    /* under-filled machine: wider groups (by the JOB's size: every shard must agree) */
     if (requested > 0) G = requested;
     for (;; G *= 2) {                                                       /* must fit with 4 warps per block */
         if (G > 32) { snprintf(g_err, sizeof g_err, "problem does not fit in shared memory (n=%d, C=%d, delta evaluation)", n, C); return -1; }
@@ -402,12 +417,19 @@ static int choose_delta_shape(int n, int C, int R, int smem_words, int n_chains,
 static void ctx_free(mhContext *c)
 {
     if (!c) return;
+    if (c->n_shards || c->shards) {                            /* multi-device parent: the shards are destroyed by the caller */
+        free(c->shards);
+        free(c->shard_first);
+        free(c);
+        return;
+    }
     void *st = c->stream;
     mhdev_free(c->d_problem, st); mhdev_free(c->d_x, st); mhdev_free(c->d_y, st); mhdev_free(c->d_rot, st); mhdev_free(c->d_cur, st);
     mhdev_free(c->d_best, st); mhdev_free(c->d_beta, st); mhdev_free(c->d_perm, st); mhdev_free(c->d_points, st);
     mhdev_free(c->d_costs, st); mhdev_free(c->d_scratch, st); mhdev_free(c->d_beta_snap, st); mhdev_free(c->d_exch_stats, st);
     for (int i = 0; i < c->n_ev; i++) { mhdev_event_destroy(c->ev[i].e0); mhdev_event_destroy(c->ev[i].e1); }
     free(c->ev);
+    mhdev_host_free(c->h_scratch);
     if (c->own_stream) mhdev_stream_destroy(c->stream);
     free(c);
 }
@@ -449,6 +471,35 @@ static void take_options(mhOptions *dst, const mhOptions *src)
     if (dst->beta_end <= 0) dst->beta_end = dst->beta_start;
 }
 
+/* Env MH_DEVICES = "all" | "0,1,5": the device list for callers whose options carry none (the reference's own
+ * entry point has no options at all).  Returns the number of devices written (0 = not set), -1 on a bad list. */
+static int devices_from_env(int32_t devices[MH_MAX_DEVICES])
+{
+    const char *env = getenv("MH_DEVICES");
+    if (!env || !*env) return 0;
+    int count = 0;
+    if (mhdev_device_count(&count) || count < 1) return 0;
+    int k = 0;
+    if (!strcmp(env, "all")) {
+        for (; k < count && k < MH_MAX_DEVICES; k++) devices[k] = k;
+        return k;
+    }
+    const char *q = env;
+    while (*q) {
+        char *end = NULL;
+        const long v = strtol(q, &end, 10);
+        if (end == q || v < 0 || v >= count || k == MH_MAX_DEVICES) {
+            snprintf(g_err, sizeof g_err, "MH_DEVICES=\"%s\": expected \"all\" or up to %d comma-separated ordinals below %d", env,
+                     MH_MAX_DEVICES, count);
+            return -1;
+        }
+        devices[k++] = (int32_t)v;
+        q = *end == ',' ? end + 1 : end;
+        if (*end && *end != ',') { snprintf(g_err, sizeof g_err, "MH_DEVICES=\"%s\": bad separator", env); return -1; }
+    }
+    return k;
+}
+
 /* rung r of every ladder starts at beta_start * (beta_end/beta_start)^(r/(T-1)) */
 static int init_betas(mhContext *c)
 {
@@ -467,23 +518,15 @@ static int init_betas(mhContext *c)
     return e;
 }
 
-MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationshipAngleStruct *rsa,
-                               const positionAndRotation *cfg, const rectangle *clearances, const rectangle *offlimits,
-                               const vertex *vertices, const vertex *surfaceRectangle, const Surface *srf, int nChains,
-                               const mhOptions *opt)
+/* One context on one device.  `o` has been through take_options; P stays the caller's. */
+static mhContext *create_single(const mhProblem *P, int nChains, const mhOptions *o)
 {
-    g_err[0] = 0;
-    mhProblem P;
     mhContext *c = NULL;
     int prev = -1, entered = 0;
-    if (nChains < 1) {
-        set_err("", "nChains must be >= 1", 0);
-        return NULL;
-    }
-    if (pack_problem(rss, rsa, cfg, clearances, offlimits, vertices, surfaceRectangle, srf, &P)) return NULL;
+    const int want = resolve_device(o);
     c = (mhContext *)calloc(1, sizeof *c);
     if (!c) { set_err("", "out of host memory", 0); goto fail; }
-    take_options(&c->opt, opt);
+    c->opt = *o;
     if (c->opt.tempering_rungs > 1) {
         if (c->opt.chain_stride == 1 &&
             (nChains % c->opt.tempering_rungs || c->opt.chain_offset % (uint64_t)c->opt.tempering_rungs)) {
@@ -497,30 +540,34 @@ MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationship
         }
         if (c->opt.exchange_interval <= 0) c->opt.exchange_interval = 100;
     }
-    c->device = c->opt.device;
-    CU(enter_device(c->device, &prev));
+    CU(enter_device(want, &prev));
     entered = 1;
-    if (c->device < 0) c->device = prev;
-    c->n = P.h->n; c->C = P.h->C; c->R = P.h->R; c->n_chains = nChains;
-    c->problem_words = P.h->total_words; c->smem_words = P.h->smem_words;
+    c->device = want < 0 ? prev : want;
+    c->n = P->h->n; c->C = P->h->C; c->R = P->h->R; c->n_chains = nChains;
+    c->problem_words = P->h->total_words; c->smem_words = P->h->smem_words;
     if (c->opt.eval_mode < MH_EVAL_FULL || c->opt.eval_mode > MH_EVAL_FULL_SCAN) { set_err("", "unknown eval_mode", 0); goto fail; }
     c->eval_internal = c->opt.eval_mode == MH_EVAL_FULL_SCAN ? 0 : c->opt.eval_mode;
     c->lanes = -1;
+    /* the lane width (and with it the float reduction order) follows the size of the WHOLE job, so that every
+     * shard of it -- another GPU, another rank, another call -- makes the same choice (mhOptions.total_chains) */
+    uint64_t job = c->opt.total_chains ? c->opt.total_chains : (uint64_t)nChains;
+    if (job < (uint64_t)nChains) job = (uint64_t)nChains;
+    const int job_chains = job > 0x7fffffffull ? 0x7fffffff : (int)job;
     if (c->opt.eval_mode == MH_EVAL_FULL && c->n >= MH_MEMO_MIN_OBJS && !getenv("MH_FULL_SCAN")) {
-        if (choose_delta_shape(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, MH_EVAL_MEMO, &c->lanes, &c->delta_warps) == 0)
+        if (choose_delta_shape(c->n, c->C, c->R, c->smem_words, job_chains, nChains, c->opt.lanes_per_chain, MH_EVAL_MEMO, &c->lanes, &c->delta_warps) == 0)
             c->eval_internal = MH_EVAL_MEMO;
         else
             c->lanes = -1;                                   /* does not fit: the plain scan needs less shared memory */
         g_err[0] = 0;
     } else if (c->eval_internal == MH_EVAL_DELTA || c->eval_internal == MH_EVAL_MEMO) {
-        if (choose_delta_shape(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, c->eval_internal, &c->lanes, &c->delta_warps)) goto fail;
+        if (choose_delta_shape(c->n, c->C, c->R, c->smem_words, job_chains, nChains, c->opt.lanes_per_chain, c->eval_internal, &c->lanes, &c->delta_warps)) goto fail;
     }
     if (c->lanes < 0) {
-        c->lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, c->eval_internal);
+        c->lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, job_chains, c->opt.lanes_per_chain, c->eval_internal);
     }
     if (c->lanes < 0) goto fail;
     /* a pinned lane width also pins the scoring kernel, so that sharded runs report identical bits */
-    c->score_lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, nChains, c->opt.lanes_per_chain, MH_EVAL_FULL);
+    c->score_lanes = choose_lanes(c->n, c->C, c->R, c->smem_words, job_chains, c->opt.lanes_per_chain, MH_EVAL_FULL);
     if (c->score_lanes < 0) goto fail;
     c->fresh = 1;
     CU(mhdev_stream_create(&c->stream));
@@ -542,17 +589,113 @@ MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationship
     CU(mhdev_malloc(&c->d_points, sizeof(point) * cn, c->stream));
     CU(mhdev_malloc(&c->d_costs, sizeof(resultCosts) * (size_t)nChains, c->stream));
     CU(mhdev_malloc(&c->d_scratch, 64, c->stream));
-    CU(mhdev_h2d(c->d_problem, P.blob, 4 * (size_t)c->problem_words, c->stream));
+    CU(mhdev_host_alloc(&c->h_scratch, 64));
+    CU(mhdev_h2d(c->d_problem, P->blob, 4 * (size_t)c->problem_words, c->stream));
     if (c->opt.tempering_rungs > 1) CU(init_betas(c));
-    CU(mhdev_stream_sync(c->stream)); /* the blob is freed below */
-    free(P.blob);
-    leave_device(c->opt.device, prev);
+    CU(mhdev_stream_sync(c->stream)); /* the caller frees the blob */
+    leave_device(want, prev);
     return c;
 fail:
-    free(P.blob);
     if (c) ctx_free(c);
-    if (entered) leave_device(opt ? opt->device : -1, prev);
+    if (entered) leave_device(want, prev);
     return NULL;
+}
+
+static void destroy_single(mhContext *ctx)
+{
+    int prev = -1;
+    const int dev = ctx->device;
+    int e = enter_device(dev, &prev);
+    if (!e) mhdev_stream_sync(ctx->stream);
+    ctx_free(ctx);
+    if (prev >= 0) leave_device(dev, prev);
+}
+
+/* mhOptions.n_devices > 1: contiguous ranges of the chains (whole ladders when tempering), one context per
+ * device.  Devices that would get no chain are left out. */
+static mhContext *create_multi(const mhProblem *P, int nChains, const mhOptions *o)
+{
+    mhContext *c = NULL;
+    const int D = o->n_devices;
+    if (o->chain_stride != 1) { set_err("", "n_devices > 1 needs chain_stride = 1 (strided shards are the one-process-per-GPU layout)", 0); return NULL; }
+    const int unit = o->tempering_rungs > 1 ? o->tempering_rungs : 1;   /* shards hold whole ladders */
+    if (nChains % unit || o->chain_offset % (uint64_t)unit) {
+        set_err("", "tempering: chain_offset and nChains must be multiples of tempering_rungs", 0);
+        return NULL;
+    }
+    for (int i = 0; i < D; i++)
+        if (o->devices[i] < 0) { snprintf(g_err, sizeof g_err, "devices[%d] = %d", i, o->devices[i]); return NULL; }
+    c = (mhContext *)calloc(1, sizeof *c);
+    if (c) {
+        c->shards = (mhContext **)calloc((size_t)D, sizeof *c->shards);
+        c->shard_first = (int *)calloc((size_t)D + 1, sizeof *c->shard_first);
+    }
+    if (!c || !c->shards || !c->shard_first) { set_err("", "out of host memory", 0); goto fail; }
+    c->opt = *o;
+    c->device = -1;
+    c->n = P->h->n; c->C = P->h->C; c->R = P->h->R; c->n_chains = nChains;
+    const int units = nChains / unit, base = units / D, rem = units % D;
+    int first = 0;
+    for (int i = 0; i < D; i++) {
+        const int count = (base + (i < rem ? 1 : 0)) * unit;
+        if (count == 0) continue;
+        mhOptions so = *o;
+        so.n_devices = 0;
+        so.device = o->devices[i];
+        so.flags |= MH_OPT_EXPLICIT_DEVICE;
+        so.chain_offset = o->chain_offset + (uint64_t)first;
+        so.total_chains = o->total_chains ? o->total_chains : (uint64_t)nChains;
+        mhContext *sc = create_single(P, count, &so);
+        if (!sc) goto fail;
+        c->shards[c->n_shards] = sc;
+        c->shard_first[c->n_shards] = first;
+        c->n_shards++;
+        first += count;
+    }
+    c->shard_first[c->n_shards] = first;
+    c->lanes = c->shards[0]->lanes; c->score_lanes = c->shards[0]->score_lanes; c->eval_internal = c->shards[0]->eval_internal;
+    return c;
+fail:
+    if (c) {
+        char keep[sizeof g_err];
+        memcpy(keep, g_err, sizeof keep);
+        for (int i = 0; i < c->n_shards; i++) destroy_single(c->shards[i]);
+        memcpy(g_err, keep, sizeof keep);
+        c->n_shards = 0;
+        if (!c->shards) c->shards = (mhContext **)calloc(1, sizeof *c->shards);   /* marks the parent for ctx_free */
+        ctx_free(c);
+    }
+    return NULL;
+}
+
+MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationshipAngleStruct *rsa,
+                               const positionAndRotation *cfg, const rectangle *clearances, const rectangle *offlimits,
+                               const vertex *vertices, const vertex *surfaceRectangle, const Surface *srf, int nChains,
+                               const mhOptions *opt)
+{
+    g_err[0] = 0;
+    mhProblem P;
+    mhOptions o;
+    if (nChains < 1) {
+        set_err("", "nChains must be >= 1", 0);
+        return NULL;
+    }
+    take_options(&o, opt);
+    if (o.n_devices < 0 || o.n_devices > MH_MAX_DEVICES) {
+        snprintf(g_err, sizeof g_err, "n_devices = %d: at most %d devices", o.n_devices, MH_MAX_DEVICES);
+        return NULL;
+    }
+    if (o.n_devices == 0 && resolve_device(&o) < 0 && o.chain_stride == 1) {
+        const int k = devices_from_env(o.devices);
+        if (k < 0) return NULL;
+        if (k > 1) o.n_devices = k;
+        else if (k == 1) { o.device = o.devices[0]; o.flags |= MH_OPT_EXPLICIT_DEVICE; }
+    }
+    if (o.n_devices == 1) { o.device = o.devices[0]; o.flags |= MH_OPT_EXPLICIT_DEVICE; o.n_devices = 0; }
+    if (pack_problem(rss, rsa, cfg, clearances, offlimits, vertices, surfaceRectangle, srf, &P)) return NULL;
+    mhContext *c = o.n_devices > 1 ? create_multi(&P, nChains, &o) : create_single(&P, nChains, &o);
+    free(P.blob);
+    return c;
 }
 
 static int push_events(mhContext *c, void **e0, void **e1)
@@ -567,11 +710,25 @@ static int push_events(mhContext *c, void **e0, void **e1)
     int e = mhdev_event_create(e0);
     if (e) return e;
     e = mhdev_event_create(e1);
-    if (e) return e;
+    if (e) {
+        mhdev_event_destroy(*e0);
+        *e0 = NULL;
+        return e;
+    }
     c->ev[c->n_ev].e0 = *e0;
     c->ev[c->n_ev].e1 = *e1;
     c->n_ev++;
     return 0;
+}
+
+/* Take back the pair push_events handed out last: the launch it was to bracket did not happen, and an event
+ * that was never recorded must not reach cudaEventElapsedTime (it would turn one failure into two). */
+static void pop_events(mhContext *c)
+{
+    if (c->n_ev == 0) return;
+    c->n_ev--;
+    mhdev_event_destroy(c->ev[c->n_ev].e0);
+    mhdev_event_destroy(c->ev[c->n_ev].e1);
 }
 
 static int drain_events(mhContext *c)
@@ -610,11 +767,15 @@ static int launch_segment(mhContext *c, int iterations, void *d_trace)
     int e = push_events(c, &e0, &e1);
     if (e) return e;
     e = mhdev_event_record(e0, c->stream);
-    if (e) return e;
-    e = mhdev_launch_chains(&L);
-    if (e) return e;
-    e = mhdev_event_record(e1, c->stream);
-    if (e) return e;
+    if (!e) {
+        const char *fault = getenv("MH_FAULT");                /* test hook: MH_FAULT=launch fails the next chain launch */
+        e = (fault && !strcmp(fault, "launch")) ? 1 /* cudaErrorInvalidValue */ : mhdev_launch_chains(&L);
+    }
+    if (!e) e = mhdev_event_record(e1, c->stream);
+    if (e) {
+        pop_events(c);
+        return e;
+    }
     c->launches++;
     c->fresh = 0;
     c->it_done += (uint64_t)iterations;
@@ -677,11 +838,62 @@ fail:
     return rc;
 }
 
-MH_API int KernelRun(mhContext *ctx, int iterations) { return run_iterations(ctx, iterations, NULL); }
+/* ---- multi-device plumbing ----------------------------------------------------------------------- */
+
+#define IS_MULTI(ctx) ((ctx)->n_shards > 0)
+
+static int multi_unsupported(const char *what)
+{
+    snprintf(g_err, sizeof g_err, "%s is not available on a multi-device context (n_devices > 1): it names ONE device's memory or stream", what);
+    return -1;
+}
+
+typedef struct shardJob {
+    mhContext *c;
+    point *points;
+    resultCosts *costs;
+    int rc;
+    char err[sizeof g_err];
+} shardJob;
+
+static int results_single(mhContext *ctx, point *points, resultCosts *costs);
+
+static void *results_worker(void *arg)
+{
+    shardJob *j = (shardJob *)arg;
+    j->rc = results_single(j->c, j->points, j->costs);
+    if (j->rc) memcpy(j->err, g_err, sizeof j->err);
+    return NULL;
+}
+
+MH_API int KernelRun(mhContext *ctx, int iterations)
+{
+    if (ctx && IS_MULTI(ctx)) {                                  /* launches are asynchronous: the devices run side by side */
+        for (int i = 0; i < ctx->n_shards; i++)
+            if (run_iterations(ctx->shards[i], iterations, NULL)) return -1;
+        return 0;
+    }
+    return run_iterations(ctx, iterations, NULL);
+}
 
 MH_API int KernelRunTraced(mhContext *ctx, int iterations, mhTraceEntry *trace)
 {
     if (!trace) { set_err("", "trace buffer is NULL", 0); return -1; }
+    if (ctx && IS_MULTI(ctx)) {                                  /* a test facility: one device after the other */
+        if (iterations < 0) { set_err("", "bad arguments", 0); return -1; }
+        for (int i = 0; i < ctx->n_shards; i++) {
+            mhContext *sc = ctx->shards[i];
+            mhTraceEntry *tmp = (mhTraceEntry *)malloc(sizeof(mhTraceEntry) * (size_t)(iterations ? iterations : 1) * (size_t)sc->n_chains);
+            if (!tmp) { set_err("", "out of host memory", 0); return -1; }
+            const int rc = run_iterations(sc, iterations, tmp);
+            for (int it = 0; !rc && it < iterations; it++)
+                memcpy(trace + (size_t)it * (size_t)ctx->n_chains + (size_t)ctx->shard_first[i], tmp + (size_t)it * (size_t)sc->n_chains,
+                       sizeof(mhTraceEntry) * (size_t)sc->n_chains);
+            free(tmp);
+            if (rc) return -1;
+        }
+        return 0;
+    }
     return run_iterations(ctx, iterations, trace);
 }
 
@@ -705,6 +917,11 @@ MH_API int KernelSynchronize(mhContext *ctx)
     int prev = -1, rc = -1;
     g_err[0] = 0;
     if (!ctx) { set_err("", "null context", 0); return -1; }
+    if (IS_MULTI(ctx)) {
+        for (int i = 0; i < ctx->n_shards; i++)
+            if (KernelSynchronize(ctx->shards[i])) return -1;
+        return 0;
+    }
     CU(enter_device(ctx->device, &prev));
     CU(mhdev_stream_sync(ctx->stream));
     rc = 0;
@@ -713,11 +930,9 @@ fail:
     return rc;
 }
 
-MH_API int KernelResults(mhContext *ctx, point *points, resultCosts *costs)
+static int results_single(mhContext *ctx, point *points, resultCosts *costs)
 {
     int prev = -1, rc = -1;
-    g_err[0] = 0;
-    if (!ctx) { set_err("", "null context", 0); return -1; }
     CU(enter_device(ctx->device, &prev));
     CU(ensure_scored(ctx));
     if (points) CU(mhdev_d2h(points, ctx->d_points, sizeof(point) * (size_t)ctx->n_chains * (size_t)ctx->n, ctx->stream));
@@ -729,11 +944,44 @@ fail:
     return rc;
 }
 
+MH_API int KernelResults(mhContext *ctx, point *points, resultCosts *costs)
+{
+    g_err[0] = 0;
+    if (!ctx) { set_err("", "null context", 0); return -1; }
+    if (!IS_MULTI(ctx)) return results_single(ctx, points, costs);
+    /* Every device copies its slice straight into the caller's one block (no collective).
+     * A device-to-pageable-host copy blocks the calling thread, so each device gets a thread of its own and
+     * the copies share the host's memory bandwidth instead of queueing behind each other. */
+    const int S = ctx->n_shards;
+    shardJob *jobs = (shardJob *)calloc((size_t)S, sizeof *jobs);
+    pthread_t *th = (pthread_t *)calloc((size_t)S, sizeof *th);
+    if (!jobs || !th) { free(jobs); free(th); set_err("", "out of host memory", 0); return -1; }
+    int rc = 0;
+    for (int i = 0; i < S; i++) {
+        jobs[i].c = ctx->shards[i];
+        jobs[i].points = points ? points + (size_t)ctx->shard_first[i] * (size_t)ctx->n : NULL;
+        jobs[i].costs = costs ? costs + ctx->shard_first[i] : NULL;
+        jobs[i].rc = -2;
+    }
+    for (int i = 1; i < S; i++)
+        if (pthread_create(&th[i], NULL, results_worker, &jobs[i])) jobs[i].rc = -3;   /* no thread: done inline below */
+    results_worker(&jobs[0]);
+    for (int i = 1; i < S; i++) {
+        if (jobs[i].rc == -3) results_worker(&jobs[i]);
+        else pthread_join(th[i], NULL);
+    }
+    for (int i = 0; i < S; i++)
+        if (jobs[i].rc) { memcpy(g_err, jobs[i].err, sizeof g_err); rc = -1; break; }
+    free(jobs); free(th);
+    return rc;
+}
+
 MH_API int KernelDeviceResults(mhContext *ctx, void **d_points, void **d_costs)
 {
     int prev = -1, rc = -1;
     g_err[0] = 0;
     if (!ctx) { set_err("", "null context", 0); return -1; }
+    if (IS_MULTI(ctx)) return multi_unsupported("KernelDeviceResults");
     CU(enter_device(ctx->device, &prev));
     CU(ensure_scored(ctx));
     if (d_points) *d_points = ctx->d_points;
@@ -748,6 +996,7 @@ MH_API int KernelSetStream(mhContext *ctx, void *stream)
 {
     g_err[0] = 0;
     if (!ctx) { set_err("", "null context", 0); return -1; }
+    if (IS_MULTI(ctx)) return multi_unsupported("KernelSetStream");
     if (KernelSynchronize(ctx)) return -1;
     if (ctx->own_stream) {
         int prev = -1;
@@ -768,24 +1017,55 @@ MH_API int KernelSetStream(mhContext *ctx, void *stream)
     return 0;
 }
 
-MH_API int KernelBest(mhContext *ctx, int *bestChain, float *bestTotal)
+/* rank key (csrc/mh_kernels.cu: rank_key) -> chain index and totalCosts; 0 = no chain */
+static int decode_rank_key(uint64_t key, float *total)
+{
+    if (!key) return -1;
+    uint32_t u = (uint32_t)(key >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    if (total) memcpy(total, &u, 4);
+    return (int)(0xFFFFFFFFu - (uint32_t)key);
+}
+
+/* Enqueue the arg-max of one context and the read-back of its key into the context's pinned scratch word. */
+static int best_enqueue(mhContext *ctx)
 {
     int prev = -1, rc = -1;
-    struct { float total; int32_t idx; } h = { 0.f, -1 };
-    g_err[0] = 0;
-    if (!ctx) { set_err("", "null context", 0); return -1; }
     CU(enter_device(ctx->device, &prev));
     CU(ensure_scored(ctx));
     CU(mhdev_launch_argmax(ctx->d_costs, ctx->n_chains, ctx->d_scratch, ctx->stream));
     ctx->launches++;
-    CU(mhdev_d2h(&h, ctx->d_scratch, sizeof h, ctx->stream));
-    CU(mhdev_stream_sync(ctx->stream));
-    if (bestChain) *bestChain = h.idx;
-    if (bestTotal) *bestTotal = h.total;
+    CU(mhdev_d2h(ctx->h_scratch, ctx->d_scratch, 8, ctx->stream));
     rc = 0;
 fail:
     if (prev >= 0) leave_device(ctx->device, prev);
     return rc;
+}
+
+MH_API int KernelBest(mhContext *ctx, int *bestChain, float *bestTotal)
+{
+    g_err[0] = 0;
+    if (!ctx) { set_err("", "null context", 0); return -1; }
+    mhContext *one[1] = { ctx };
+    mhContext **list = IS_MULTI(ctx) ? ctx->shards : one;
+    const int S = IS_MULTI(ctx) ? ctx->n_shards : 1;
+    for (int i = 0; i < S; i++)                                 /* every device reduces at the same time ... */
+        if (best_enqueue(list[i])) return -1;
+    int best = -1;
+    float best_total = 0.f;
+    for (int i = 0; i < S; i++) {                               /* ... and the host compares at most 8 keys */
+        if (KernelSynchronize(list[i])) return -1;
+        float t = 0.f;
+        const int idx = decode_rank_key(*(const uint64_t *)list[i]->h_scratch, &t);
+        if (idx < 0) continue;
+        if (best < 0 || t > best_total) {                       /* shards are in chain order: a tie stays with the lower id */
+            best = (IS_MULTI(ctx) ? ctx->shard_first[i] : 0) + idx;
+            best_total = t;
+        }
+    }
+    if (bestChain) *bestChain = best;
+    if (bestTotal) *bestTotal = best_total;
+    return 0;
 }
 
 typedef struct rankItem { float total; int32_t chain; } rankItem;
@@ -797,67 +1077,117 @@ static int rank_cmp(const void *a, const void *b)
     return x->chain < y->chain ? -1 : (x->chain > y->chain);
 }
 
-MH_API int KernelTopK(mhContext *ctx, int k, int *chains, float *totals)
+#define MH_TOPK_DEVICE_MAX 512 /* kTopkMaxK of mh_kernels.cu */
+
+/* The k best chains of ONE context into items[0..k), best first.  k <= 512: sorted on the device (tiles of 1024
+ * rank keys, bitonic in shared memory, survivors merged stage by stage), only k keys cross PCIe; larger k:
+ * every total is read back and sorted here. */
+static int topk_single(mhContext *ctx, int k, rankItem *items)
 {
     int prev = -1, rc = -1;
+    void *d_work = NULL, *d_out = NULL;
+    uint64_t *hk = NULL;
     resultCosts *hc = NULL;
-    rankItem *items = NULL;
+    rankItem *all = NULL;
+    if (k > ctx->n_chains) k = ctx->n_chains;
+    CU(enter_device(ctx->device, &prev));
+    CU(ensure_scored(ctx));
+    if (k <= MH_TOPK_DEVICE_MAX) {
+        hk = (uint64_t *)malloc(8 * (size_t)k);
+        if (!hk) { set_err("", "out of host memory", 0); goto fail; }
+        CU(mhdev_malloc(&d_work, 16 * (size_t)mhdev_topk_work_items(ctx->n_chains, k), ctx->stream));
+        CU(mhdev_malloc(&d_out, 8 * (size_t)k, ctx->stream));
+        CU(mhdev_launch_topk(ctx->d_costs, ctx->n_chains, k, d_work, d_out, ctx->stream));
+        ctx->launches++;
+        CU(mhdev_d2h(hk, d_out, 8 * (size_t)k, ctx->stream));
+        CU(mhdev_stream_sync(ctx->stream));
+        for (int i = 0; i < k; i++) items[i].chain = decode_rank_key(hk[i], &items[i].total);
+    } else {
+        hc = (resultCosts *)malloc(sizeof(resultCosts) * (size_t)ctx->n_chains);
+        all = (rankItem *)malloc(sizeof(rankItem) * (size_t)ctx->n_chains);
+        if (!hc || !all) { set_err("", "out of host memory", 0); goto fail; }
+        CU(mhdev_d2h(hc, ctx->d_costs, sizeof(resultCosts) * (size_t)ctx->n_chains, ctx->stream));
+        CU(mhdev_stream_sync(ctx->stream));
+        for (int i = 0; i < ctx->n_chains; i++) { all[i].total = hc[i].totalCosts; all[i].chain = i; }
+        qsort(all, (size_t)ctx->n_chains, sizeof(rankItem), rank_cmp);
+        memcpy(items, all, sizeof(rankItem) * (size_t)k);
+    }
+    rc = k;
+fail:
+    if (d_work || d_out) { mhdev_stream_sync(ctx->stream); mhdev_free(d_work, ctx->stream); mhdev_free(d_out, ctx->stream); }
+    free(hk); free(hc); free(all);
+    if (prev >= 0) leave_device(ctx->device, prev);
+    return rc;
+}
+
+MH_API int KernelTopK(mhContext *ctx, int k, int *chains, float *totals)
+{
     g_err[0] = 0;
     if (!ctx || k < 1) { set_err("", "bad arguments", 0); return -1; }
     if (k > ctx->n_chains) k = ctx->n_chains;
-    hc = (resultCosts *)malloc(sizeof(resultCosts) * (size_t)ctx->n_chains);
-    items = (rankItem *)malloc(sizeof(rankItem) * (size_t)ctx->n_chains);
-    if (!hc || !items) { set_err("", "out of host memory", 0); goto fail; }
-    CU(enter_device(ctx->device, &prev));
-    CU(ensure_scored(ctx));
-    CU(mhdev_d2h(hc, ctx->d_costs, sizeof(resultCosts) * (size_t)ctx->n_chains, ctx->stream));
-    CU(mhdev_stream_sync(ctx->stream));
-    for (int i = 0; i < ctx->n_chains; i++) { items[i].total = hc[i].totalCosts; items[i].chain = i; }
-    qsort(items, (size_t)ctx->n_chains, sizeof(rankItem), rank_cmp);
+    const int S = IS_MULTI(ctx) ? ctx->n_shards : 1;
+    rankItem *items = (rankItem *)malloc(sizeof(rankItem) * (size_t)k * (size_t)S);
+    if (!items) { set_err("", "out of host memory", 0); return -1; }
+    int have = 0;
+    if (IS_MULTI(ctx)) {                                         /* the k best of every device, merged here */
+        for (int i = 0; i < S; i++) {
+            const int m = topk_single(ctx->shards[i], k, items + have);
+            if (m < 0) { free(items); return -1; }
+            for (int j = 0; j < m; j++) items[have + j].chain += ctx->shard_first[i];
+            have += m;
+        }
+        qsort(items, (size_t)have, sizeof(rankItem), rank_cmp);
+    } else {
+        have = topk_single(ctx, k, items);
+        if (have < 0) { free(items); return -1; }
+    }
+    if (k > have) k = have;
     for (int i = 0; i < k; i++) {
         if (chains) chains[i] = items[i].chain;
         if (totals) totals[i] = items[i].total;
     }
-    rc = k;
-fail:
-    free(hc); free(items);
-    if (prev >= 0) leave_device(ctx->device, prev);
-    return rc;
+    free(items);
+    return k;
 }
 
 MH_API int KernelTopKDistinct(mhContext *ctx, int k, float minDistance, float rotWeight, int *chains, float *totals)
 {
     int prev = -1, rc = -1, found = 0;
-    float *d_mind = NULL, *fill = NULL;
+    float *d_mind = NULL;
+    void *d_keys = NULL;
+    uint64_t *hk = NULL;
     g_err[0] = 0;
     if (!ctx || k < 1 || !(minDistance >= 0.f) || !(rotWeight >= 0.f)) { set_err("", "bad arguments", 0); return -1; }
+    if (IS_MULTI(ctx)) return multi_unsupported("KernelTopKDistinct (the layouts to compare live on different devices)");
     if (k > ctx->n_chains) k = ctx->n_chains;
+    hk = (uint64_t *)malloc(8 * (size_t)k);
+    if (!hk) { set_err("", "out of host memory", 0); return -1; }
     CU(enter_device(ctx->device, &prev));
     CU(ensure_scored(ctx));
-    /* d_mind = +inf: 0x7f800000 cannot be memset bytewise, so it is copied from the host once */
-    fill = (float *)malloc(sizeof(float) * (size_t)ctx->n_chains);
-    if (!fill) { set_err("", "out of host memory", 0); goto fail; }
-    for (int i = 0; i < ctx->n_chains; i++) fill[i] = INFINITY;
+    /* k rounds enqueued back to back: round r reads round r-1's pick on the device, updates every chain's distance
+     * to the picks so far and arg-maxes what is still far enough (one fused kernel per round); ONE read-back of
+     * the k picks at the end instead of a blocking 8-byte copy per pick */
     CU(mhdev_malloc((void **)&d_mind, sizeof(float) * (size_t)ctx->n_chains, ctx->stream));
-    CU(mhdev_h2d(d_mind, fill, sizeof(float) * (size_t)ctx->n_chains, ctx->stream));
-    for (found = 0; found < k; found++) {
-        struct { float total; int chain; } best;
-        CU(mhdev_launch_pick_distinct(ctx->d_costs, d_mind, ctx->n_chains, found ? minDistance : -1.0f, ctx->d_scratch, ctx->stream));
-        CU(mhdev_d2h(&best, ctx->d_scratch, sizeof best, ctx->stream));
-        CU(mhdev_stream_sync(ctx->stream));
+    CU(mhdev_malloc(&d_keys, 8 * (size_t)k, ctx->stream));
+    CU(mhdev_memset(d_keys, 0, 8 * (size_t)k, ctx->stream));
+    for (int r = 0; r < k; r++) {
+        CU(mhdev_launch_distinct_round(ctx->d_costs, ctx->d_points, ctx->n, ctx->n_chains, r, minDistance, rotWeight, (float)(2 * MH_PI),
+                                       d_mind, d_keys, ctx->stream));
         ctx->launches++;
-        if (best.chain < 0) break;                              /* every remaining chain is a near-duplicate */
-        if (chains) chains[found] = best.chain;
-        if (totals) totals[found] = best.total;
-        if (found + 1 < k) {
-            CU(mhdev_launch_distance(ctx->d_points, ctx->n, ctx->n_chains, best.chain, rotWeight, (float)(2 * MH_PI), d_mind, ctx->stream));
-            ctx->launches++;
-        }
+    }
+    CU(mhdev_d2h(hk, d_keys, 8 * (size_t)k, ctx->stream));
+    CU(mhdev_stream_sync(ctx->stream));
+    for (found = 0; found < k; found++) {
+        float t = 0.f;
+        const int idx = decode_rank_key(hk[found], &t);
+        if (idx < 0) break;                                     /* every remaining chain is a near-duplicate */
+        if (chains) chains[found] = idx;
+        if (totals) totals[found] = t;
     }
     rc = found;
 fail:
-    if (d_mind) { mhdev_stream_sync(ctx->stream); mhdev_free(d_mind, ctx->stream); }
-    free(fill);
+    if (d_mind || d_keys) { mhdev_stream_sync(ctx->stream); mhdev_free(d_mind, ctx->stream); mhdev_free(d_keys, ctx->stream); }
+    free(hk);
     if (prev >= 0) leave_device(ctx->device, prev);
     return rc;
 }
@@ -867,10 +1197,16 @@ MH_API int KernelBestKey(mhContext *ctx, void *d_key)
     int prev = -1, rc = -1;
     g_err[0] = 0;
     if (!ctx || !d_key) { set_err("", "bad arguments", 0); return -1; }
+    if (IS_MULTI(ctx)) return multi_unsupported("KernelBestKey");
+    /* the key keeps 32 bits of the global chain id */
+    if (ctx->opt.chain_offset + (uint64_t)(ctx->n_chains - 1) * ctx->opt.chain_stride > 0xFFFFFFFFull) {
+        set_err("", "KernelBestKey: this context holds global chain ids >= 2^32, the packed key keeps 32 bits", 0);
+        return -1;
+    }
     CU(enter_device(ctx->device, &prev));
     CU(ensure_scored(ctx));
     CU(mhdev_launch_argmax(ctx->d_costs, ctx->n_chains, ctx->d_scratch, ctx->stream));
-    CU(mhdev_launch_bestkey(ctx->d_scratch, ctx->opt.chain_offset, 1, d_key, ctx->stream));
+    CU(mhdev_launch_bestkey(ctx->d_scratch, ctx->opt.chain_offset, ctx->opt.chain_stride, d_key, ctx->stream));
     ctx->launches += 2;
     rc = 0;
 fail:
@@ -891,6 +1227,11 @@ MH_API int KernelReset(mhContext *ctx)
 {
     g_err[0] = 0;
     if (!ctx) { set_err("", "null context", 0); return -1; }
+    if (IS_MULTI(ctx)) {
+        for (int i = 0; i < ctx->n_shards; i++)
+            if (KernelReset(ctx->shards[i])) return -1;
+        return 0;
+    }
     ctx->fresh = 1;
     ctx->it_done = 0;
     ctx->costs_dirty = 1;
@@ -910,6 +1251,7 @@ MH_API int KernelReset(mhContext *ctx)
 MH_API int KernelTemperingState(mhContext *ctx, void **d_totals, void **d_betas)
 {
     g_err[0] = 0;
+    if (ctx && IS_MULTI(ctx)) return multi_unsupported("KernelTemperingState");
     if (!ctx || ctx->opt.tempering_rungs <= 1) { set_err("", "context has no tempering ladder", 0); return -1; }
     if (d_totals) *d_totals = ctx->d_cur;
     if (d_betas) *d_betas = ctx->d_beta;
@@ -920,6 +1262,7 @@ MH_API int KernelTemperingExchange(mhContext *ctx, const void *d_all_totals, con
 {
     int prev = -1, rc = -1;
     g_err[0] = 0;
+    if (ctx && IS_MULTI(ctx)) return multi_unsupported("KernelTemperingExchange");
     if (!ctx || ctx->opt.tempering_rungs <= 1 || !d_all_totals || !d_all_betas) { set_err("", "bad arguments", 0); return -1; }
     const uint64_t ex = (uint64_t)ctx->opt.exchange_interval;
     const uint64_t gnow = ctx->opt.iteration_offset + ctx->it_done;
@@ -942,6 +1285,17 @@ MH_API int KernelTemperingStats(mhContext *ctx, long long *attempts, long long *
     g_err[0] = 0;
     if (!ctx || ctx->opt.tempering_rungs <= 1) { set_err("", "context has no tempering ladder", 0); return -1; }
     const int pairs = ctx->opt.tempering_rungs - 1;
+    if (IS_MULTI(ctx)) {                                         /* whole ladders per device: the counts add up */
+        long long *a = (long long *)calloc(2 * (size_t)pairs + 2, sizeof *a);
+        if (!a) { set_err("", "out of host memory", 0); return -1; }
+        for (int r = 0; r < pairs; r++) { if (attempts) attempts[r] = 0; if (accepted) accepted[r] = 0; }
+        for (int i = 0; i < ctx->n_shards; i++) {
+            if (KernelTemperingStats(ctx->shards[i], a, a + pairs) != pairs) { free(a); return -1; }
+            for (int r = 0; r < pairs; r++) { if (attempts) attempts[r] += a[r]; if (accepted) accepted[r] += a[pairs + r]; }
+        }
+        free(a);
+        return pairs;
+    }
     h = (unsigned long long *)malloc(16 * (size_t)ctx->opt.tempering_rungs);
     if (!h) { set_err("", "out of host memory", 0); return -1; }
     CU(enter_device(ctx->device, &prev));
@@ -963,6 +1317,20 @@ MH_API int KernelStats(mhContext *ctx, double *kernel_ms, long long *launches)
     int prev = -1, rc = -1;
     g_err[0] = 0;
     if (!ctx) { set_err("", "null context", 0); return -1; }
+    if (IS_MULTI(ctx)) {                                         /* concurrent devices: the slowest one's time, everybody's launches */
+        double ms_max = 0;
+        long long total = 0;
+        for (int i = 0; i < ctx->n_shards; i++) {
+            double ms = 0;
+            long long l = 0;
+            if (KernelStats(ctx->shards[i], &ms, &l)) return -1;
+            if (ms > ms_max) ms_max = ms;
+            total += l;
+        }
+        if (kernel_ms) *kernel_ms = ms_max;
+        if (launches) *launches = total;
+        return 0;
+    }
     CU(enter_device(ctx->device, &prev));
     CU(drain_events(ctx));
     if (kernel_ms) *kernel_ms = ctx->kernel_ms;
@@ -973,15 +1341,39 @@ fail:
     return rc;
 }
 
+MH_API int KernelShape(mhContext *ctx, int *lanesPerChain, int *evalForm, int *nDevices, int *deviceOrdinals, int *chainsPerDevice)
+{
+    g_err[0] = 0;
+    if (!ctx) { set_err("", "null context", 0); return -1; }
+    if (lanesPerChain) *lanesPerChain = ctx->lanes;
+    if (evalForm) *evalForm = ctx->eval_internal == 0 ? MH_EVAL_FULL_SCAN : ctx->eval_internal;
+    const int S = IS_MULTI(ctx) ? ctx->n_shards : 1;
+    if (nDevices) *nDevices = S;
+    for (int i = 0; i < MH_MAX_DEVICES; i++) {
+        if (deviceOrdinals) deviceOrdinals[i] = i < S ? (IS_MULTI(ctx) ? ctx->shards[i]->device : ctx->device) : -1;
+        if (chainsPerDevice) chainsPerDevice[i] = i < S ? (IS_MULTI(ctx) ? ctx->shards[i]->n_chains : ctx->n_chains) : 0;
+    }
+    return 0;
+}
+
+MH_API int KernelDeviceCount(void)
+{
+    int count = 0;
+    g_err[0] = 0;
+    const int e = mhdev_device_count(&count);
+    if (e) { set_err("%s failed: %s", "device count", e); return -1; }
+    return count;
+}
+
 MH_API void KernelDestroy(mhContext *ctx)
 {
     if (!ctx) return;
-    int prev = -1;
-    const int dev = ctx->device;
-    int e = enter_device(dev, &prev);
-    if (!e) mhdev_stream_sync(ctx->stream);
-    ctx_free(ctx);
-    if (prev >= 0) leave_device(dev, prev);
+    if (IS_MULTI(ctx)) {
+        for (int i = 0; i < ctx->n_shards; i++) destroy_single(ctx->shards[i]);
+        ctx_free(ctx);
+        return;
+    }
+    destroy_single(ctx);
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -1015,9 +1407,17 @@ MH_API result *KernelWrapperEx(const relationshipStruct *rss, const relationship
     clock_gettime(CLOCK_MONOTONIC, &ts[2]);
     if (KernelRun(c, iterations)) goto fail;
     prefault(pts, sizeof(point) * (size_t)chains * (size_t)n); /* overlaps with the kernel, which is asynchronous */
+    /* MH_PIN_RESULT=1: page-lock the (malloc'd, caller-owned) result block in place for the duration of the copy,
+     * also while the kernel runs; the copy then runs at pinned-memory speed and, on a multi-device context, truly
+     * concurrently.  Off by default: measured in profiles/ (registration cost against copy time). */
+    int pinned = 0;
+    if (getenv("MH_PIN_RESULT") && sizeof(point) * (size_t)chains * (size_t)n >= (1u << 20))
+        pinned = mhdev_host_register(pts, sizeof(point) * (size_t)chains * (size_t)n) == 0;
     if (timing) KernelSynchronize(c);
     clock_gettime(CLOCK_MONOTONIC, &ts[3]);
-    if (KernelResults(c, pts, costs)) goto fail;
+    const int res_rc = KernelResults(c, pts, costs);
+    if (pinned) mhdev_host_unregister(pts);
+    if (res_rc) goto fail;
     clock_gettime(CLOCK_MONOTONIC, &ts[4]);
     for (int i = 0; i < chains; i++) {
         res[i].points = pts + (size_t)i * (size_t)n; /* Kernel.cu:981 */

@@ -101,15 +101,24 @@ int mhdev_launch_exchange(int n_chains, uint64_t chain_offset, uint64_t chain_st
                           uint64_t it_last, uint64_t seed, const float *d_all_total, const float *d_all_beta,
                           uint64_t gather_base, uint64_t gather_stride, uint64_t gather_local, float *d_beta,
                           void *d_stats /* uint64[2*rungs] {attempts, accepted} per pair (lower rung), or NULL */, void *stream);
-/* arg-max of totalCosts over the context's chains: d_out = {float total, int32 chain}. */
-int mhdev_launch_argmax(const void *d_costs, int n_chains, void *d_out, void *stream);
-/* Distinct suggestions: d_mind[chain] = min(d_mind[chain], distance of the chain's layout to ref_chain's);
- * then the best chain with d_mind > min_dist: d_out = {float total, int32 chain or -1}. */
-int mhdev_launch_distance(const void *d_points, int n, int n_chains, int ref_chain, float rot_weight, float two_pi, float *d_mind,
-                          void *stream);
-int mhdev_launch_pick_distinct(const void *d_costs, const float *d_mind, int n_chains, float min_dist, void *d_out, void *stream);
-/* d_key (device int64) = order-preserving (totalCosts, global chain id) key of the arg-max result. */
-int mhdev_launch_bestkey(const void *d_argmax_out, uint64_t chain_offset, uint64_t chain_stride, void *d_key, void *stream);
+/* Rank keys.  A chain's rank key is the unsigned 64-bit word  orderable(totalCosts) << 32 | (0xFFFFFFFF - chain):
+ * an unsigned MAX over keys is the arg-max of totalCosts with ties going to the lower chain index; 0 = "no
+ * chain".  (mh_rank_key / mhdev_decode_rank_key) */
+/* arg-max of totalCosts over the context's chains, many blocks, one atomicMax per block: *d_key (device
+ * uint64, zeroed by this call) = the best chain's rank key. */
+int mhdev_launch_argmax(const void *d_costs, int n_chains, void *d_key, void *stream);
+/* Top-k by rank key, on the device: d_out[0..k) = the k largest rank keys in descending order (k <= 512).
+ * d_work: 2 * mhdev_topk_work_items(n_chains, k) uint64 of scratch. */
+int mhdev_topk_work_items(int n_chains, int k);
+int mhdev_launch_topk(const void *d_costs, int n_chains, int k, void *d_work, void *d_out, void *stream);
+/* Distinct suggestions, round r of k (all rounds are enqueued back to back, no host round trip): the chain
+ * picked in round r-1 is read from d_keys[r-1] ON THE DEVICE; every chain's d_mind = min(d_mind, distance to
+ * that pick's layout) (round 0: d_mind = +inf); then d_keys[r] = rank key of the best chain with
+ * d_mind > min_dist.  d_keys[0..k) must be zeroed before round 0. */
+int mhdev_launch_distinct_round(const void *d_costs, const void *d_points, int n, int n_chains, int round, float min_dist,
+                                float rot_weight, float two_pi, float *d_mind, void *d_keys, void *stream);
+/* d_key (device int64) = order-preserving (totalCosts, GLOBAL chain id) key of the arg-max rank key. */
+int mhdev_launch_bestkey(const void *d_rank_key, uint64_t chain_offset, uint64_t chain_stride, void *d_key, void *stream);
 /* Largest dynamic shared memory per block and SM count / clock of the current device. */
 int mhdev_device_limits(int *max_smem_per_block, int *max_smem_per_sm, int *sm_count, int *clock_khz, int *cc_major,
                         int *cc_minor, char *name, int name_len);
@@ -117,6 +126,7 @@ int mhdev_device_limits(int *max_smem_per_block, int *max_smem_per_sm, int *sm_c
 int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int eval_mode, int warps);
 
 /* raw runtime helpers */
+int mhdev_device_count(int *count);
 int mhdev_get_device(int *dev);
 int mhdev_set_device(int dev);
 int mhdev_malloc(void **p, size_t bytes, void *stream); /* stream-ordered, from the library's pool */
@@ -135,6 +145,8 @@ int mhdev_event_record(void *ev, void *stream);
 int mhdev_event_elapsed_ms(void *e0, void *e1, float *ms); /* synchronises on e1 */
 int mhdev_host_alloc(void **p, size_t bytes);               /* pinned staging memory */
 void mhdev_host_free(void *p);
+int mhdev_host_register(void *p, size_t bytes);             /* page-lock caller memory in place (portable) */
+void mhdev_host_unregister(void *p);
 const char *mhdev_error_string(int code);
 
 #ifdef __cplusplus

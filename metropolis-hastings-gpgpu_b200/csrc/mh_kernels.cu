@@ -10,7 +10,9 @@
 // mh_score_kernel<G>   all eight cost terms of given layouts (fills resultCosts, which the
 //                      reference forgets -- quirk Q3; also the KernelEvalCosts parity hook).
 // mh_exchange_kernel   replica exchange between neighbouring temperature rungs (extension).
-// mh_argmax_kernel     best chain of a context.
+// mh_argmax_kernel, mh_topk_stage_kernel, mh_distinct_round_kernel, mh_bestkey_kernel
+//                      ranking of a context's chains on the device (best, top-k, distinct top-k, the packed
+//                      key of the multi-GPU arg-best).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -565,102 +567,139 @@ __global__ void mh_exchange_kernel(int n_chains, uint64_t chain_offset, uint64_t
     }
 }
 
-__global__ void mh_argmax_kernel(const Costs8 *__restrict__ costs, int n, float *out_total, int *out_idx)
+// ---- ranking on the device -----------------------------------------------------------------------------
+// A chain's rank key: orderable(totalCosts) << 32 | (0xFFFFFFFF - chain).  An unsigned MAX over keys is the
+// arg-max of totalCosts (the sampler maximises it, quirk Q10) with ties going to the lower chain index;
+// 0 means "no chain".  -0.0 ranks as +0.0, a NaN below everything.
+__device__ __forceinline__ unsigned long long rank_key(float total, int chain)
 {
-    __shared__ float sv[32];
-    __shared__ int si[32];
-    float bv = -INFINITY;
-    int bi = -1;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float v = costs[i].total;
-        if (v > bv || bi < 0) { bv = v; bi = i; }
-    }
+    uint32_t u = __float_as_uint(total + 0.0f);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    if (total != total) u = 1u;
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)chain);
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
+{
+#pragma unroll
     for (int m = 16; m > 0; m >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, m);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-        if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, m);
+        v = o > v ? o : v;
     }
-    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    return v;
+}
+
+// Block maximum -> one atomicMax on *dst (256-thread blocks).
+__device__ __forceinline__ void block_max_to(unsigned long long v, unsigned long long *dst)
+{
+    __shared__ unsigned long long sm[8];
+    v = warp_max_u64(v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x < 32) {
-        const int nw = (blockDim.x + 31) / 32;
-        bv = threadIdx.x < nw ? sv[threadIdx.x] : -INFINITY;
-        bi = threadIdx.x < nw ? si[threadIdx.x] : -1;
-        for (int m = 16; m > 0; m >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, m);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-            if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
-        }
-        if (threadIdx.x == 0) { *out_total = bv; *out_idx = bi; }
+        v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0ull;
+        v = warp_max_u64(v);
+        if (threadIdx.x == 0 && v) atomicMax(dst, v);
     }
 }
 
-// Distinct suggestions (KernelTopKDistinct).  How far is every chain's layout from a reference chain's?  The
-// distance of two layouts is the largest displacement of any object, max_i max(|dx|, |dy|, rot_weight |drot|)
-// with the rotation difference wrapped into [0, PI]; mind[chain] keeps the minimum over the references seen
-// so far.  One warp per chain, lanes over objects.
-__global__ void mh_distance_kernel(const PointRec *__restrict__ points, int n, int n_chains, int ref_chain, float rot_weight, float two_pi,
-                                   float *__restrict__ mind)
+// arg-max of totalCosts over a context's chains: many blocks, one atomic per block (the round-1 kernel was a
+// single 1024-thread block: 39 us at 65536 chains, 150 us at 262144, on the time-to-best-cost polling path).
+__global__ void __launch_bounds__(256) mh_argmax_kernel(const Costs8 *__restrict__ costs, int n, unsigned long long *key)
 {
-    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (chain >= n_chains) return;
-    const PointRec *a = points + (size_t)chain * n, *b = points + (size_t)ref_chain * n;
-    float d = 0.f;
-    for (int i = lane; i < n; i += 32) {
-        const PointRec p = a[i], q = b[i];
-        float dr = fabsf(p.rotY - q.rotY);
-        dr = fminf(dr, fabsf(two_pi - dr));
-        d = fmaxf(d, fmaxf(fmaxf(fabsf(p.x - q.x), fabsf(p.y - q.y)), rot_weight * dr));
+    unsigned long long best = 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long k = rank_key(costs[i].total, i);
+        best = k > best ? k : best;
     }
-    for (int m = 16; m > 0; m >>= 1)
-        d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, m));
-    if (lane == 0) mind[chain] = fminf(mind[chain], d);
+    block_max_to(best, key);
 }
 
-// The chain with the highest totalCosts among those farther than min_dist from every reference so far
-// (ties: lower index); out = {total, index}, index -1 if none is left.
-__global__ void mh_pick_distinct_kernel(const Costs8 *__restrict__ costs, const float *__restrict__ mind, int n, float min_dist,
-                                        float *out_total, int *out_idx)
+// Top-k by rank key.  One stage: every block sorts a tile of kTopkTile keys (bitonic, shared memory, descending)
+// and keeps its k largest; stages repeat on the survivors until one tile is left, whose first k are the answer.
+constexpr int kTopkTile = 1024, kTopkThreads = 512, kTopkMaxK = 512;
+
+__global__ void __launch_bounds__(kTopkThreads) mh_topk_stage_kernel(const Costs8 *__restrict__ costs, const unsigned long long *__restrict__ in,
+                                                                     int n_in, int k, unsigned long long *__restrict__ out)
 {
-    __shared__ float sv[32];
-    __shared__ int si[32];
-    float bv = -INFINITY;
-    int bi = -1;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float v = costs[i].total;
-        if (mind[i] > min_dist && (bi < 0 || v > bv)) { bv = v; bi = i; }
+    __shared__ unsigned long long t[kTopkTile];
+    const int base = blockIdx.x * kTopkTile;
+    for (int j = threadIdx.x; j < kTopkTile; j += kTopkThreads) {
+        const int i = base + j;
+        unsigned long long v = 0ull;
+        if (i < n_in) v = costs ? rank_key(costs[i].total, i) : in[i];
+        t[j] = v;
     }
-    for (int m = 16; m > 0; m >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, m);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-        if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
-    }
-    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
     __syncthreads();
-    if (threadIdx.x < 32) {
-        const int nw = (blockDim.x + 31) / 32;
-        bv = threadIdx.x < nw ? sv[threadIdx.x] : -INFINITY;
-        bi = threadIdx.x < nw ? si[threadIdx.x] : -1;
-        for (int m = 16; m > 0; m >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, m);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-            if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    for (int size = 2; size <= kTopkTile; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int j = threadIdx.x;                          // compare-exchange number j of kTopkTile / 2
+            const int lo = 2 * j - (j & (stride - 1));          // index of the pair's lower element
+            const int hi = lo + stride;
+            const bool desc = (lo & size) == 0;                 // direction of this bitonic run
+            const unsigned long long a = t[lo], b = t[hi];
+            if ((a < b) == desc) { t[lo] = b; t[hi] = a; }
+            __syncthreads();
         }
-        if (threadIdx.x == 0) { *out_total = bv; *out_idx = bi; }
     }
+    for (int j = threadIdx.x; j < k; j += kTopkThreads)
+        out[(size_t)blockIdx.x * k + j] = t[j];
+}
+
+// Distinct suggestions (KernelTopKDistinct), round `round`.  The distance of two layouts is the largest
+// displacement of any object, max_i max(|dx|, |dy|, rot_weight |drot|) with the rotation difference wrapped into
+// [0, PI]; mind[chain] keeps the minimum over the picks so far.  One warp per chain, lanes over objects.  The
+// previous round's pick is read from keys[round - 1] on the device, so the host enqueues all rounds at once.
+__global__ void __launch_bounds__(256) mh_distinct_round_kernel(const Costs8 *__restrict__ costs, const PointRec *__restrict__ points, int n,
+                                                                int n_chains, int round, float min_dist, float rot_weight, float two_pi,
+                                                                float *__restrict__ mind, unsigned long long *keys)
+{
+    int ref = -1;
+    if (round > 0) {
+        const unsigned long long pk = keys[round - 1];
+        if (pk == 0ull) return;                                 // nothing was left in the previous round (uniform over the grid)
+        ref = (int)(0xFFFFFFFFu - (uint32_t)pk);
+    }
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long best = 0ull;
+    for (int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chain < n_chains; chain += warps) {
+        float m = INFINITY;
+        if (round > 0) {
+            const PointRec *a = points + (size_t)chain * n, *b = points + (size_t)ref * n;
+            float d = 0.f;
+            for (int i = lane; i < n; i += 32) {
+                const PointRec p = a[i], q = b[i];
+                float dr = fabsf(p.rotY - q.rotY);
+                dr = fminf(dr, fabsf(two_pi - dr));
+                d = fmaxf(d, fmaxf(fmaxf(fabsf(p.x - q.x), fabsf(p.y - q.y)), rot_weight * dr));
+            }
+            for (int s = 16; s > 0; s >>= 1)
+                d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, s));
+            m = fminf(mind[chain], d);
+        }
+        if (lane == 0) {
+            mind[chain] = m;
+            if (round == 0 || m > min_dist) {
+                const unsigned long long k = rank_key(costs[chain].total, chain);
+                best = k > best ? k : best;
+            }
+        }
+    }
+    block_max_to(best, keys + round);
 }
 
 // Packs the context's best chain for a MAX all-reduce: NCCL has no arg-max, so the totalCosts
 // (made order-preserving as an unsigned integer) goes in the high word and the complemented
-// global chain id in the low word (ties go to the lower id); the top bit is flipped so that a
+// GLOBAL chain id in the low word (ties go to the lower id); the top bit is flipped so that a
 // SIGNED 64-bit MAX orders the keys correctly.
-__global__ void mh_bestkey_kernel(const float *__restrict__ best_total, const int *__restrict__ best_idx, uint64_t chain_offset,
-                                  uint64_t chain_stride, long long *__restrict__ key)
+__global__ void mh_bestkey_kernel(const unsigned long long *__restrict__ rank, uint64_t chain_offset, uint64_t chain_stride,
+                                  long long *__restrict__ key)
 {
-    uint32_t u = __float_as_uint(*best_total);
-    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    const uint64_t g = chain_offset + (uint64_t)(*best_idx) * chain_stride;
-    const uint64_t k = ((uint64_t)u << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)g);
+    const unsigned long long rk = *rank;
+    const uint32_t idx = 0xFFFFFFFFu - (uint32_t)rk;
+    const uint64_t g = chain_offset + (uint64_t)idx * chain_stride;
+    const uint64_t k = (rk & 0xFFFFFFFF00000000ull) | (uint64_t)(0xFFFFFFFFu - (uint32_t)g);
     *key = (long long)(k ^ 0x8000000000000000ull);
 }
 
@@ -786,35 +825,65 @@ int mhdev_launch_exchange(int n_chains, uint64_t chain_offset, uint64_t chain_st
     return (int)cudaGetLastError();
 }
 
-int mhdev_launch_argmax(const void *d_costs, int n_chains, void *d_out, void *stream)
+static int rank_grid(long long threads_wanted)
 {
-    mh::mh_argmax_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const mh::Costs8 *>(d_costs), n_chains,
-                                                                           static_cast<float *>(d_out),
-                                                                           reinterpret_cast<int *>(static_cast<float *>(d_out) + 1));
+    long long blocks = (threads_wanted + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int mhdev_launch_argmax(const void *d_costs, int n_chains, void *d_key, void *stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(d_key, 0, 8, st);
+    if (e != cudaSuccess) return (int)e;
+    mh::mh_argmax_kernel<<<rank_grid(n_chains), 256, 0, st>>>(static_cast<const mh::Costs8 *>(d_costs), n_chains,
+                                                              static_cast<unsigned long long *>(d_key));
     return (int)cudaGetLastError();
 }
 
-int mhdev_launch_distance(const void *d_points, int n, int n_chains, int ref_chain, float rot_weight, float two_pi, float *d_mind,
-                          void *stream)
+int mhdev_topk_work_items(int n_chains, int k)
 {
-    const long long threads = (long long)n_chains * 32;
-    mh::mh_distance_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const mh::PointRec *>(d_points), n, n_chains, ref_chain, rot_weight, two_pi, d_mind);
+    const int tiles = (n_chains + mh::kTopkTile - 1) / mh::kTopkTile;
+    return tiles * (k < 1 ? 1 : k);
+}
+
+int mhdev_launch_topk(const void *d_costs, int n_chains, int k, void *d_work, void *d_out, void *stream)
+{
+    if (k < 1 || k > mh::kTopkMaxK) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int items = mhdev_topk_work_items(n_chains, k);
+    unsigned long long *w[2] = { static_cast<unsigned long long *>(d_work), static_cast<unsigned long long *>(d_work) + items };
+    const mh::Costs8 *costs = static_cast<const mh::Costs8 *>(d_costs);
+    const unsigned long long *in = nullptr;
+    int n_in = n_chains, side = 0;
+    for (;;) {
+        const int tiles = (n_in + mh::kTopkTile - 1) / mh::kTopkTile;
+        unsigned long long *out = tiles == 1 ? static_cast<unsigned long long *>(d_out) : w[side];
+        mh::mh_topk_stage_kernel<<<tiles, mh::kTopkThreads, 0, st>>>(costs, in, n_in, k, out);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+        if (tiles == 1) return 0;
+        costs = nullptr;
+        in = out;
+        n_in = tiles * k;
+        side ^= 1;
+    }
+}
+
+int mhdev_launch_distinct_round(const void *d_costs, const void *d_points, int n, int n_chains, int round, float min_dist,
+                                float rot_weight, float two_pi, float *d_mind, void *d_keys, void *stream)
+{
+    mh::mh_distinct_round_kernel<<<rank_grid((long long)n_chains * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const mh::Costs8 *>(d_costs), static_cast<const mh::PointRec *>(d_points), n, n_chains, round, min_dist, rot_weight,
+        two_pi, d_mind, static_cast<unsigned long long *>(d_keys));
     return (int)cudaGetLastError();
 }
 
-int mhdev_launch_pick_distinct(const void *d_costs, const float *d_mind, int n_chains, float min_dist, void *d_out, void *stream)
+int mhdev_launch_bestkey(const void *d_rank_key, uint64_t chain_offset, uint64_t chain_stride, void *d_key, void *stream)
 {
-    mh::mh_pick_distinct_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const mh::Costs8 *>(d_costs), d_mind, n_chains, min_dist, static_cast<float *>(d_out),
-        reinterpret_cast<int *>(static_cast<float *>(d_out) + 1));
-    return (int)cudaGetLastError();
-}
-
-int mhdev_launch_bestkey(const void *d_argmax_out, uint64_t chain_offset, uint64_t chain_stride, void *d_key, void *stream)
-{
-    const float *f = static_cast<const float *>(d_argmax_out);
-    mh::mh_bestkey_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(f, reinterpret_cast<const int *>(f + 1), chain_offset,
+    mh::mh_bestkey_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned long long *>(d_rank_key), chain_offset,
                                                                         chain_stride, static_cast<long long *>(d_key));
     return (int)cudaGetLastError();
 }
@@ -841,6 +910,7 @@ int mhdev_device_limits(int *max_smem_per_block, int *max_smem_per_sm, int *sm_c
     return 0;
 }
 
+int mhdev_device_count(int *count) { return (int)cudaGetDeviceCount(count); }
 int mhdev_get_device(int *dev) { return (int)cudaGetDevice(dev); }
 int mhdev_set_device(int dev) { return (int)cudaSetDevice(dev); }
 
@@ -940,6 +1010,8 @@ int mhdev_event_elapsed_ms(void *e0, void *e1, float *ms)
 }
 int mhdev_host_alloc(void **p, size_t bytes) { return (int)cudaMallocHost(p, bytes ? bytes : 16); }
 void mhdev_host_free(void *p) { if (p) cudaFreeHost(p); }
+int mhdev_host_register(void *p, size_t bytes) { return (int)cudaHostRegister(p, bytes, cudaHostRegisterPortable); }
+void mhdev_host_unregister(void *p) { if (p) cudaHostUnregister(p); }
 const char *mhdev_error_string(int code) { return cudaGetErrorString(static_cast<cudaError_t>(code)); }
 
 } // extern "C"

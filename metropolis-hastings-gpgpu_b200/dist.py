@@ -6,6 +6,15 @@ the end of a run: NCCL has no MINLOC/MAXLOC, so each rank packs (order-preservin
 complemented global chain id) into one signed 64-bit key on its device (KernelBestKey), the
 keys are MAX-all-reduced (8 bytes), and the owner of the winning chain broadcasts its n x 24 B
 layout.  torch.distributed is plumbing only; the packing and the arg-max run in libKernel.so.
+
+Bit-identity of a sharded run with the unsharded one needs every shard to use the same lane width (it fixes
+the float reduction order): create the contexts with `total_chains=` the size of the whole job (shard_options
+below does), and the library picks the width from that instead of from the shard's own count.
+
+Stream ordering: a context runs on a non-blocking stream of its own unless KernelSetStream says otherwise, and
+torch / NCCL work on torch's current stream.  The helpers below put the context on torch's current stream
+(`ctx.set_stream`) before they touch its device buffers, so that kernel -> collective -> kernel is ordered
+without a host synchronisation.
 """
 import numpy as np
 
@@ -16,6 +25,13 @@ def shard(total_chains, rank, world):
     count = base + (1 if rank < rem else 0)
     offset = rank * base + min(rank, rem)
     return offset, count
+
+
+def shard_options(total_chains, rank, world):
+    """(chain count, mhOptions keywords) of rank's shard: contiguous global chain ids, and the job's size so
+    that every shard picks the lane width the unsharded job would."""
+    offset, count = shard(total_chains, rank, world)
+    return count, {"chain_offset": offset, "total_chains": total_chains}
 
 
 def owner_of(global_chain, total_chains, world):
@@ -47,9 +63,20 @@ def device_view(ptr, nbytes, device):
     return torch.as_tensor(DeviceBytes(ptr, nbytes), device=device)
 
 
+def _on_torch_stream(ctx):
+    """Run the context on torch's current stream (idempotent): everything torch enqueues afterwards is ordered
+    after the context's kernels and vice versa."""
+    import torch
+    h = torch.cuda.current_stream().cuda_stream
+    if getattr(ctx, "_stream_handle", None) != h:
+        ctx.set_stream(h)
+        ctx._stream_handle = h
+
+
 def global_best(kernel, ctx, n, offset, total_chains, rank, world, device, dist=None):
     """Returns (global chain id, totalCosts, layout bytes tensor of n*24 B) on every rank."""
     import torch
+    _on_torch_stream(ctx)
     key = torch.zeros(1, dtype=torch.int64, device=device)
     ctx.best_key(key.data_ptr())
     if dist is not None and world > 1:
@@ -74,6 +101,7 @@ def tempering_epoch(ctxs_or_ctx, iterations, device, dist=None, world=1):
     import torch
     ctxs = ctxs_or_ctx if isinstance(ctxs_or_ctx, (list, tuple)) else [ctxs_or_ctx]
     for ctx in ctxs:
+        _on_torch_stream(ctx)
         ctx.run(iterations)
     tots, bets = [], []
     for ctx in ctxs:

@@ -10,8 +10,10 @@ PI = 3.1416  # Kernel.cu:31 (quirk Q4)
 
 
 def _dt(fields, itemsize):
-    names, formats, offsets = zip(*fields)
-    return np.dtype({"names": list(names), "formats": list(formats), "offsets": list(offsets), "itemsize": itemsize})
+    names = [f[0] for f in fields]
+    formats = [(f[1], f[3]) if len(f) > 3 else f[1] for f in fields]
+    offsets = [f[2] for f in fields]
+    return np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": itemsize})
 
 
 vertex = _dt([("x", "<f8", 0), ("y", "<f8", 8), ("z", "<f8", 16)], 24)
@@ -53,9 +55,12 @@ mhOptions = _dt(
     [("struct_size", "<u4", 0), ("flags", "<u4", 4), ("seed", "<u8", 8), ("chain_offset", "<u8", 16), ("iteration_offset", "<u8", 24),
      ("beta_start", "<f8", 32), ("beta_end", "<f8", 40), ("schedule", "<i4", 48), ("schedule_length", "<i4", 52),
      ("result_mode", "<i4", 56), ("eval_mode", "<i4", 60), ("lanes_per_chain", "<i4", 64), ("device", "<i4", 68),
-     ("tempering_rungs", "<i4", 72), ("exchange_interval", "<i4", 76), ("chain_stride", "<u8", 80)],
-    88,
+     ("tempering_rungs", "<i4", 72), ("exchange_interval", "<i4", 76), ("chain_stride", "<u8", 80),
+     ("total_chains", "<u8", 88), ("n_devices", "<i4", 96), ("devices", "<i4", 100, (8,)), ("reserved0", "<i4", 132)],
+    136,
 )
+MH_OPT_EXPLICIT_DEVICE = 1
+MH_MAX_DEVICES = 8
 mhTraceEntry = _dt(
     [("move", "<i4", 0), ("obj1", "<i4", 4), ("obj2", "<i4", 8), ("accepted", "<i4", 12), ("star_total", "<f4", 16),
      ("cur_total", "<f4", 20), ("u", "<f4", 24), ("beta", "<f4", 28)],

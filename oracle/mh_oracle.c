@@ -21,10 +21,14 @@
  *
  * Parity pin: the cost functions are checked bit-for-bit on this host against the
  * reference's own source compiled as host C++ (oracle/_ref/libref_costs_host.so, built by
- * oracle/Makefile from the reference tree in place) -- tests/test_oracle_vs_ref.py -- and
+ * oracle/Makefile from the reference tree in place) -- tests/test_oracle.py::
+ * test_bit_exact_against_reference_host_build -- and
  * against the committed golden vectors that library produced (tests/golden/).  The RNG is
  * pinned to the Random123 known-answer vectors for Philox4x32-10.  The proposal stream as
- * a whole is "parity unpinned" against the reference by construction (wall-clock seed).
+ * a whole is "parity unpinned" against the reference by construction (wall-clock seed); what
+ * propose() and Accept() DO with their draws is pinned distributionally against the reference's
+ * own device functions (oracle/ref_gpu_harness.cu: RefProposeGPU / RefAcceptGPU;
+ * tests/test_propose_parity.py).
  *
  * Build: gcc -O2 -fopenmp -shared -fPIC (oracle/Makefile).  -ffp-contract=off is REQUIRED so
  * that no a*b+c is fused: the reference's host build does not fuse either.

@@ -3,7 +3,14 @@ line.  Test/baseline infrastructure.  Always launched as a subprocess with a tim
 and the probes: the unmodified reference deadlocks on sm_70+ for blockxDim > 1 (divergent
 __syncthreads, Kernel.cu:747 under Kernel.cu:819), and a hang must not take the caller down.
 
-usage: ref_runner.py <variant: plain|nb> <config id> <chains> <iterations> <blockxDim> <warmup> <steps>
+usage: ref_runner.py <variant: plain|nb> <config id> <chains> <iterations> <blockxDim> <warmup> <steps> [finals.npy]
+
+Reports the whole-call rate (what a caller of the reference sees: its H2D/D2H, its initRNG launch and its
+kernel), the device-event time of the whole call, and the device time of the initRNG launch alone
+(Kernel.cu:939-943, measured by RefInitRngMs at the same launch shape) so that the kernel-only rate can be
+quoted without the RNG set-up.  With a last argument, the oracle's totalCosts of the layouts the reference
+returned are saved there (the reference's own `costs` are uninitialised memory, quirk Q3): the sample of the
+informational KS test against the reference kernel.
 """
 import ctypes as C
 import importlib
@@ -22,6 +29,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def main():
     variant, cid, chains, iters, block, warmup, steps = sys.argv[1], *map(int, sys.argv[2:8])
+    finals_path = sys.argv[8] if len(sys.argv) > 8 else None
     pkg = importlib.import_module("metropolis-hastings-gpgpu_b200")
     import oracle_lib
     path = os.path.join(ROOT, "oracle", "_ref", "libKernel_ref_nb.so" if variant == "nb" else "libKernel_ref.so")
@@ -45,7 +53,11 @@ def main():
         lay[f] = pts[f].reshape(-1)
     finite = bool(np.isfinite(pts["x"]).all() and np.isfinite(pts["rotY"]).all())
     tot = o.costs_batch(room, lay)["totalCosts"] if finite else np.array([np.nan])
-    print(json.dumps({"variant": variant, "config": cid, "chains": chains, "iterations": iters, "block": block, "heap_rc": rc,
+    if finals_path:
+        np.save(finals_path, tot)
+    init_ms = float(np.median([ref.init_rng_ms(chains, block) for _ in range(3)]))
+    print(json.dumps({"init_rng_ms": init_ms, "proposals_per_s_dev_without_init_rng": chains * iters / max(float(np.mean(dev)) - init_ms * 1e-3, 1e-9),
+                      "variant": variant, "config": cid, "chains": chains, "iterations": iters, "block": block, "heap_rc": rc,
                       "wall_s": float(np.mean(wall)), "dev_s": float(np.mean(dev)), "proposals_per_s": chains * iters / float(np.mean(wall)),
                       "finite": finite, "mean_total": float(np.mean(tot)), "initial_total": float(o.costs(room)["totalCosts"])}), flush=True)
 

@@ -26,12 +26,12 @@ def _has_gpu():
 
 def test_numpy_mirrors_match_header_sizes():
     assert L.check_layout()
-    assert L.mhOptions.itemsize == 88 and L.mhTraceEntry.itemsize == 32
+    assert L.mhOptions.itemsize == 136 and L.mhTraceEntry.itemsize == 32
 
 
 def test_headers_compile_as_c_and_cpp(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "mh_kernel.h"\nint main(void){return (int)sizeof(mhOptions) - 88;}\n')
+    src.write_text('#include "mh_kernel.h"\nint main(void){return (int)sizeof(mhOptions) - 136;}\n')
     for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++11")):
         exe = tmp_path / ("t_" + cc)
         subprocess.run([cc, std, "-x", "c" if cc == "gcc" else "c++", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
@@ -52,6 +52,33 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     assert exported == declared, exported ^ declared        # nothing else leaks out of the library
+
+
+def test_every_export_has_a_ctypes_signature():
+    """A context handle is a 64-bit pointer; without argtypes ctypes passes a bare Python int as a 32-bit C int
+    and a handle above 4 GiB is truncated.  Every export must declare its signature."""
+    k = pkg.Kernel()
+    for name in pkg.binding.EXPORTS:
+        fn = getattr(k.lib, name)
+        assert fn.argtypes is not None, name
+    for name in ("KernelWrapper", "KernelWrapperEx", "KernelCreate"):
+        assert getattr(k.lib, name).restype is C.c_void_p, name
+    # a handle with the high bits set must arrive whole: KernelShape(NULL-ish bogus) is never called, but the
+    # marshalling of a 64-bit value through argtypes can be checked without a device
+    big = 0x7F12_3456_789A
+    assert C.c_void_p(big).value == big
+
+
+def test_options_struct_grows_compatibly():
+    """mhOptions carries struct_size: the round-1 layout (88 bytes) is a prefix of the current one, field for field."""
+    r1 = ["struct_size", "flags", "seed", "chain_offset", "iteration_offset", "beta_start", "beta_end", "schedule", "schedule_length",
+          "result_mode", "eval_mode", "lanes_per_chain", "device", "tempering_rungs", "exchange_interval", "chain_stride"]
+    assert list(L.mhOptions.names[:len(r1)]) == r1
+    assert L.mhOptions.fields["chain_stride"][1] == 80 and L.mhOptions.fields["total_chains"][1] == 88
+    assert L.mhOptions.fields["n_devices"][1] == 96 and L.mhOptions.fields["devices"][1] == 100
+    o = pkg.binding.make_options(devices=[2, 0, 1], device=0)
+    assert int(o["n_devices"][0]) == 3 and list(o["devices"][0][:3]) == [2, 0, 1] and int(o["flags"][0]) & L.MH_OPT_EXPLICIT_DEVICE
+    assert int(pkg.binding.make_options()["device"][0]) == -1
 
 
 def test_oracle_is_not_linked_into_the_product():

@@ -3,12 +3,14 @@ oracle (oracle/mh_oracle.c, pinned bit-for-bit to the reference's own cost code)
 seeded inputs, and against the golden vectors the reference's code produced.
 
 Tolerance.  north_star: every cost term within 1e-5 relative of the reference's cost function.
-The kernel is float32; the reference mixes float and double, so a term
-that is a SUM with cancellation cannot be held to 1e-5 of its own (possibly tiny) value: each
-term is compared with rtol 1e-5 plus an absolute floor of 1e-5 x the natural scale of that term
-(n for the per-object sums, the sum of |weighted terms| for the total).  The pair-wise angle term
-has jump discontinuities (Kernel.cu:245-254); layouts within 1e-4 rad of a jump are compared on
-the other terms only (oracle_angle_branch_margin)."""
+Wherever a term is at least a tenth of its natural scale (n for the per-object sums, the sum of
+|weighted terms| for the total: term_scales) it is held to PURE rtol = 1e-5.  Below that -- a sum
+that happens to be tiny cannot be held to 1e-5 of itself by a float32 evaluation of a mixed
+float/double expression -- an absolute floor of 1e-5 x scale is added.  The
+worst and 99.9th-percentile errors actually observed over 1e5 layouts per room are committed in
+profiles/parity_errors_r2.json (tools/parity_errors.py).  The pair-wise angle term has jump
+discontinuities (Kernel.cu:245-254); layouts within 1e-4 rad of a jump are compared on the other
+terms only (oracle_angle_branch_margin)."""
 import importlib
 import json
 import os
@@ -46,7 +48,7 @@ def assert_costs_close(room, got, ref, skip_pair=None, rtol=RTOL):
         if skip_pair is not None and f in ("PairWiseCosts", "totalCosts"):
             g, r = g[~skip_pair], r[~skip_pair]
         err = np.abs(g - r)
-        tol = rtol * np.abs(r) + rtol * sc[f]
+        tol = rtol * np.abs(r) + np.where(np.abs(r) > 0.1 * sc[f], 0.0, rtol * sc[f])
         bad = err > tol
         assert not bad.any(), f"{f}: {bad.sum()} of {len(r)} off, worst {err.max():.3e} (ref {r[np.argmax(err)]:.6e})"
 
@@ -249,43 +251,6 @@ def test_resume_continues_the_same_stream(kernel):
     assert pa.tobytes() == pb.tobytes() and ca.tobytes() == cb.tobytes()
 
 
-def test_final_cost_distribution_matches_oracle_ks(kernel, oracle):
-    """Two-sample KS on the final totalCosts of 4096 chains, kernel vs oracle, disjoint seeds."""
-    for cid, iters in ((1, 400), (2, 300)):
-        room = S.make_config(cid)
-        _, ck = kernel.wrapper_ex(room, 4096, iters, seed=2024)
-        _, co = oracle.run(room, 4096, iters, seed=4048)
-        p = stats.ks_2samp(ck["totalCosts"], co["totalCosts"]).pvalue
-        assert p > 0.01, (cid, p)
-        # and the same seed gives near-identical populations (most chains never hit a tie)
-        _, cs = oracle.run(room, 512, iters, seed=2024)
-        same = np.isclose(ck["totalCosts"][:512], cs["totalCosts"], rtol=1e-4, atol=1e-3).mean()
-        assert same > 0.8, same
-
-
-def test_final_cost_distribution_config3_ks(kernel, oracle):
-    """BASELINE config 3 (the headline room, 50 objects, all terms): two-sample KS on the final
-    totalCosts of 4096 chains after 250 iterations, kernel vs oracle with disjoint seeds, and on each
-    of the weighted terms (SURVEY.md section 8d "statistical parity")."""
-    room = S.make_config(3)
-    _, ck = kernel.wrapper_ex(room, 4096, 250, seed=777)
-    _, co = oracle.run(room, 4096, 250, seed=1555)
-    for f in ("totalCosts", "SymmetryCosts", "ClearanceCosts", "PairWiseCosts", "FocalPointCosts", "SurfaceAreaCosts"):
-        p = stats.ks_2samp(ck[f], co[f]).pvalue
-        assert p > 0.005, (f, p)
-
-
-def test_final_cost_distribution_config4_ks(kernel, oracle):
-    """BASELINE config 4 (200 objects; the default runs the memo form with clearance row sums, 32 lanes per
-    chain): two-sample KS on the final totalCosts, default and delta evaluation against the oracle."""
-    room = S.make_config(4)
-    _, co = oracle.run(room, 1024, 100, seed=31337)
-    _, ck = kernel.wrapper_ex(room, 1024, 100, seed=4242)
-    _, cd = kernel.wrapper_ex(room, 1024, 100, seed=4343, eval_mode=1)
-    assert stats.ks_2samp(ck["totalCosts"], co["totalCosts"]).pvalue > 0.01
-    assert stats.ks_2samp(cd["totalCosts"], co["totalCosts"]).pvalue > 0.01
-
-
 def test_frozen_objects_and_passthrough(kernel):
     room = S.make_config(1)
     room.cfg["frozen"][[1, 6]] = 1
@@ -316,9 +281,7 @@ def test_best_mode_and_annealing(kernel, oracle):
     _, ca = kernel.wrapper_ex(room, 4096, 600, seed=3, beta_start=0.5, beta_end=16.0, schedule=1)
     _, c2 = kernel.wrapper_ex(room, 4096, 600, seed=3)
     assert ca["totalCosts"].mean() > c2["totalCosts"].mean()
-    _, oa = oracle.run(room, 4096, 600, seed=4, beta_start=0.5, beta_end=16.0, schedule=1)
-    assert stats.ks_2samp(ca["totalCosts"], oa["totalCosts"]).pvalue > 0.01      # 0.87 when written (tools/ks_margins.py)
-    _, os_ = oracle.run(room, 512, 600, seed=3, beta_start=0.5, beta_end=16.0, schedule=1)
+    _, os_ = oracle.run(room, 512, 600, seed=3, beta_start=0.5, beta_end=16.0, schedule=1)          # (distribution: test_ks_parity.py)
     assert np.isclose(ca["totalCosts"][:512], os_["totalCosts"], rtol=1e-4, atol=1e-3).mean() > 0.9
 
 
@@ -403,10 +366,7 @@ def test_parallel_tempering_matches_oracle(kernel, oracle):
     assert (tr["beta"][20:] != tr["beta"][:1]).any()       # exchanges do happen
     assert np.mean(tr["beta"] == otr["beta"]) > 0.85
     assert np.mean(tr["accepted"] == otr["accepted"]) > 0.85
-    # populations: the coldest rung ends higher than the hottest (the sampler maximises, Q10)
-    _, ck = kernel.wrapper_ex(room, 2048, 400, **opts)
-    _, co = oracle.run(room, 2048, 400, **dict(opts, seed=14))
-    assert stats.ks_2samp(ck["totalCosts"], co["totalCosts"]).pvalue > 0.01
+    # (populations: tests/test_ks_parity.py::test_parallel_tempering)
 
 
 def test_tempering_exchange_statistics(kernel):
@@ -496,23 +456,6 @@ def test_delta_follows_the_full_evaluation_trajectory(kernel):
     np.testing.assert_allclose(td["star_total"][:, c], tf["star_total"][:, c], rtol=1e-4, atol=1e-2)
 
 
-def test_delta_distribution_matches_oracle_ks(kernel, oracle):
-    for cid, iters in ((1, 400), (2, 300)):
-        room = S.make_config(cid)
-        _, ck = kernel.wrapper_ex(room, 4096, iters, seed=2025, eval_mode=1)
-        _, co = oracle.run(room, 4096, iters, seed=5050)
-        assert stats.ks_2samp(ck["totalCosts"], co["totalCosts"]).pvalue > 0.01, cid
-
-
-def test_delta_distribution_config3_ks(kernel, oracle):
-    """Delta evaluation on the 50-object room (8 lanes per chain, the shape the bench reports) against the
-    oracle's full evaluation: final totalCosts of 4096 chains, disjoint seeds, two-sample KS."""
-    room = S.make_config(3)
-    _, ck = kernel.wrapper_ex(room, 4096, 260, seed=100, eval_mode=1)        # (tools/ks_delta_check.py: p = 0.12 .. 0.97 over
-    _, co = oracle.run(room, 4096, 260, seed=9000)                           #  eight seed pairs, equal to the full form's)
-    assert stats.ks_2samp(ck["totalCosts"], co["totalCosts"]).pvalue > 0.01
-
-
 def test_memo_mode_with_annealing_and_resume(kernel):
     """The memo form under a geometric beta schedule, split over two calls, against the plain scan."""
     room = S.make_config(3)
@@ -536,9 +479,6 @@ def test_delta_with_frozen_best_and_annealing(kernel, oracle):
     _, cf = kernel.wrapper_ex(room, 256, 300, seed=9, eval_mode=1)
     pb, cb = kernel.wrapper_ex(room, 256, 300, seed=9, eval_mode=1, result_mode=1)
     assert np.all(cb["totalCosts"] >= cf["totalCosts"] - 1e-2)
-    _, ca = kernel.wrapper_ex(room, 4096, 600, seed=3, eval_mode=1, beta_start=0.5, beta_end=16.0, schedule=1)
-    _, oa = oracle.run(room, 4096, 600, seed=4, beta_start=0.5, beta_end=16.0, schedule=1)
-    assert stats.ks_2samp(ca["totalCosts"], oa["totalCosts"]).pvalue > 0.01
 
 
 def test_cross_gpu_tempering_equals_single_context(kernel):

@@ -191,3 +191,21 @@ def test_bit_exact_against_reference_on_wild_rooms(oracle):
         b, rb = ref.costs(room, raw=True)
         assert a.tobytes() == b.tobytes(), seed
         assert ra.tobytes() == rb.tobytes(), seed
+
+
+def test_committed_ks_samples_are_the_oracles_own_chains(oracle):
+    """tests/golden/ks_oracle_finals.npz (the long-horizon oracle samples of tests/test_ks_parity.py) pinned to the
+    oracle's code: a chain depends only on (seed, global chain id), so re-running a few chains of every sample
+    must reproduce the committed rows bit for bit."""
+    path = os.path.join(HERE, "golden", "ks_oracle_finals.npz")
+    z = np.load(path)
+    for cid in (3, 4):
+        chains, iters = (int(v) for v in z[f"cfg{cid}_plan"])
+        room = S.make_config(cid)
+        for i, seed in enumerate(z["oracle_seeds"]):
+            rows = z[f"cfg{cid}_seed{int(seed)}"]
+            assert rows.shape == (chains, len(L.COST_FIELDS)) and np.isfinite(rows).all()
+            first = (37 * (i + 1)) % (chains - 2)
+            _, c = oracle.run(room, 2, iters, seed=int(seed), chain_offset=first)
+            got = np.stack([c[f] for f in L.COST_FIELDS], 1).astype(np.float32)
+            assert got.tobytes() == rows[first:first + 2].tobytes(), (cid, int(seed))
