@@ -245,6 +245,28 @@ MH_API int KernelTemperingExchange(mhContext *ctx, const void *d_all_totals, con
  * pair that hardly ever swaps is a gap in the ladder; one that always swaps is a rung too many.  Returns
  * rungs-1 or -1. */
 MH_API int KernelTemperingStats(mhContext *ctx, long long *attempts, long long *accepted);
+/* Ladder tuning (the policy layer on top of the statistics).  The reference has one fixed
+ * BETA (Kernel.cu:33); a tempering ladder only works when neighbouring rungs exchange often enough, and the
+ * geometric ladder mhOptions describes is a starting guess.
+ *   KernelTemperingLadder        the context's current ladder, betas[rungs], rung 0 first.  Returns rungs or -1.
+ *   KernelTemperingProposeLadder a pure function, no context: from the current ladder and the exchange counts of
+ *                                every pair of neighbouring rungs (summed over all ranks when the ladder is spread
+ *                                over GPUs) it places the interior rungs so that every pair is expected to exchange
+ *                                equally often: the gap (in log beta) of pair r is taken to carry a "distance"
+ *                                -log(acceptance_r) (a pair that always swaps is close, one that never swaps is
+ *                                far; rates are clamped to [0.01, 0.99], pairs with fewer than 8 attempts count as
+ *                                0.5), and the new rungs sit at equal steps of the cumulative distance, linearly in
+ *                                log beta inside a gap.  End points stay.  `damping` in (0, 1] moves only that
+ *                                fraction of the way (1 = all the way).  Returns 0 or -1.
+ *   KernelTemperingSetLadder     re-targets every chain from the current ladder to betas[rungs]: a chain that
+ *                                sits on rung r (whichever chain that currently is: exchanges permute them) moves
+ *                                to betas[r]; clears the exchange statistics.  Asynchronous on the context's stream.
+ * Changing the ladder mid-run breaks detailed balance for that step: adapt during burn-in, then leave it. */
+MH_API int KernelTemperingLadder(mhContext *ctx, double *betas);
+MH_API int KernelTemperingProposeLadder(int rungs, const double *current, const long long *attempts, const long long *accepted,
+                                        double damping, double *proposed);
+MH_API int KernelTemperingSetLadder(mhContext *ctx, const double *betas);
+
 /* Milliseconds the device spent in the MH kernels since creation (CUDA events) and how many
  * kernels were launched.  Multi-device context: the devices run concurrently, kernel_ms is the largest
  * per-device sum and launches the total over the devices. */

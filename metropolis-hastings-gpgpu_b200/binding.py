@@ -19,7 +19,7 @@ EXPORTS = ("KernelWrapper", "KernelWrapperEx", "KernelFree", "KernelLastError", 
            "KernelRunTraced", "KernelSynchronize", "KernelResults", "KernelDeviceResults", "KernelSetStream", "KernelBest",
            "KernelStats", "KernelDestroy", "KernelDeviceInfo", "KernelBestKey", "KernelDecodeBestKey", "KernelReset", "KernelTrim",
            "KernelTemperingState", "KernelTemperingExchange", "KernelTopK", "KernelTopKDistinct", "KernelTemperingStats", "KernelShape",
-           "KernelDeviceCount")
+           "KernelDeviceCount", "KernelTemperingLadder", "KernelTemperingProposeLadder", "KernelTemperingSetLadder")
 
 
 class KernelError(RuntimeError):
@@ -106,6 +106,9 @@ class Kernel:
                 "KernelTemperingStats": (I, [_P, _P, _P]),
                 "KernelShape": (I, [_P, PI_, PI_, PI_, _P, _P]),
                 "KernelDeviceCount": (I, []),
+                "KernelTemperingLadder": (I, [_P, _P]),
+                "KernelTemperingProposeLadder": (I, [I, _P, _P, _P, D, _P]),
+                "KernelTemperingSetLadder": (I, [_P, _P]),
             }
             assert set(sig) == set(EXPORTS)
             for name, (res, args) in sig.items():
@@ -209,6 +212,16 @@ class Kernel:
             self._fail("KernelDeviceCount")
         return n
 
+    def propose_ladder(self, current, attempts, accepted, damping=1.0):
+        """KernelTemperingProposeLadder: the ladder that would equalise the exchange rates of neighbouring rungs."""
+        cur = np.ascontiguousarray(current, np.float64)
+        att = np.ascontiguousarray(attempts, np.int64)
+        acc = np.ascontiguousarray(accepted, np.int64)
+        out = np.zeros(len(cur), np.float64)
+        if self.lib.KernelTemperingProposeLadder(len(cur), _ptr(cur), _ptr(att), _ptr(acc), float(damping), _ptr(out)) != 0:
+            self._fail("KernelTemperingProposeLadder")
+        return out
+
     def create(self, room, n_chains, **opts):
         return Context(self, room, n_chains, **opts)
 
@@ -289,6 +302,17 @@ class Context:
         if self.k.lib.KernelTemperingStats(self.h, _ptr(att), _ptr(acc)) != rungs - 1:
             self.k._fail("KernelTemperingStats")
         return att, acc
+
+    def ladder(self, rungs):
+        out = np.zeros(rungs, np.float64)
+        if self.k.lib.KernelTemperingLadder(self.h, _ptr(out)) != rungs:
+            self.k._fail("KernelTemperingLadder")
+        return out
+
+    def set_ladder(self, betas):
+        b = np.ascontiguousarray(betas, np.float64)
+        if self.k.lib.KernelTemperingSetLadder(self.h, _ptr(b)) != 0:
+            self.k._fail("KernelTemperingSetLadder")
 
     def reset(self):
         if self.k.lib.KernelReset(self.h) != 0:

@@ -31,7 +31,7 @@
 
 #define MH_TLS __thread
 #define MH_MEMO_MIN_OBJS 28 /* nObjs from which MH_EVAL_FULL runs in its bit-identical memo form (measured: -7 % at 24, -2 % at 26, +10 % at 28, +19 % at 32, +27 % at 50, 2.2x at 100, 3.4x at 200) */
-#define MH_MAX_BLOCKS_PER_SM 5 /* 128-thread blocks at the chain kernel's register cap (MH_MIN_BLOCKS in mh_kernels.cu) */
+#define MH_MAX_BLOCKS_PER_SM 4 /* 128-thread blocks at the chain kernel's register cap (MH_MIN_BLOCKS in mh_kernels.cu) */
 
 static MH_TLS char g_err[512];
 
@@ -97,9 +97,43 @@ static void rect_consts(const vertex *v, int start, float box[4], float *v0x)
     *v0x = (float)v[start].x; /* quirk Q6 */
 }
 
+/* Fixed-point scale of the clearance term.  ClearanceCosts (Kernel.cu:404-434) is evaluated as an INTEGER sum of
+ * rectangle overlaps: coordinates in units of 2^-k, areas in units of 2^-2k, 64-bit accumulator.  Integer addition
+ * is associative, so the sum does not depend on the order of its terms -- which is what lets a proposal update it
+ * by the few pairs it touches and still hold, bit for bit, the value a from-scratch evaluation computes.
+ * k is the largest exponent for which nothing can overflow:
+ *   coordinates: every box coordinate is (rectangle constant) + (position), |.| <= E + P, and must stay below 2^30;
+ *   the sum    : at most C*n overlaps, each at most (widest possible box: 2(E + P), quirk Q6 makes boxes as wide as
+ *                the position) x (tallest rectangle), must stay below 2^62.
+ * P bounds every position a chain can visit: the room's AABB (translations clamp to it, Kernel.cu:616-633), the
+ * caller's layout(s) (swaps only permute positions).  At the BASELINE rooms k = 21..24, i.e. 5e-7 .. 6e-8 length
+ * units -- the float32 evaluation it replaces had ulp(8.0) = 9.5e-7 on the same coordinates. */
+static int clearance_scale(double pos_bound, double rect_bound, double rect_height, int n, int C)
+{
+    const double ext = pos_bound + rect_bound + 1.0;
+    int k1 = 30 - (int)ceil(log2(ext));
+    const double worst_area = (double)(C > 0 ? C : 1) * (double)n * (2.0 * ext) * (rect_height + 1e-9);
+    int k2 = (int)floor((62.0 - log2(worst_area > 1.0 ? worst_area : 1.0)) / 2.0);
+    int k = k1 < k2 ? k1 : k2;
+    if (k > 30) k = 30;
+    if (k < -30) k = -30;
+    return k;
+}
+
+static int32_t to_fixed(double v, double scale)
+{
+    const double r = nearbyint(v * scale);
+    if (r > 2147483647.0) return 2147483647;
+    if (r < -2147483648.0) return (int32_t)(-2147483647 - 1);
+    return (int32_t)r;
+}
+
+/* extra_layouts / n_extra: further layouts (n objects each) whose positions the fixed-point scale must cover
+ * (KernelEvalCosts evaluates layouts no chain produced) */
 static int pack_problem(const relationshipStruct *rss, const relationshipAngleStruct *rsa, const positionAndRotation *cfg,
                         const rectangle *clearances, const rectangle *offlimits, const vertex *vertices,
-                        const vertex *surfaceRectangle, const Surface *srf, mhProblem *out)
+                        const vertex *surfaceRectangle, const Surface *srf, const positionAndRotation *extra_layouts, int n_extra,
+                        mhProblem *out)
 {
     out->blob = NULL;
     if (!srf || !cfg || !offlimits || !vertices || !surfaceRectangle) {
@@ -155,6 +189,10 @@ static int pack_problem(const relationshipStruct *rss, const relationshipAngleSt
     H.off_clr_adj = w;    w = align4(w + C);
     H.off_rel_adj_off = w; w = align4(w + n + 1);
     H.off_rel_adj = w;    w = align4(w + 4 * R);
+    H.off_obj_boxq = w;   w += 4 * n;
+    H.off_clr_boxq = w;   w += 4 * C;
+    H.off_obj_v0xq = w;   w = align4(w + n);
+    H.off_clr_v0xq = w;   w = align4(w + C);
     H.smem_words = w;
     H.off_cfg0 = w;       w = align4(w + 3 * n);
     H.off_pass = w;       w = align4(w + 3 * n);
@@ -210,8 +248,36 @@ static int pack_problem(const relationshipStruct *rss, const relationshipAngleSt
     }
     H.denom = denom;
     H.any_free = any_free;
+    {   /* fixed-point clearance term: scale from the bounds of positions and rectangles, then the integer constants */
+        double pos_bound = fmax(fmax(fabs((double)H.room_minx), fabs((double)H.room_maxx)), fmax(fabs((double)H.room_miny), fabs((double)H.room_maxy)));
+        for (int i = 0; i < n; i++) pos_bound = fmax(pos_bound, fmax(fabs(cfg[i].x), fabs(cfg[i].y)));
+        for (long long i = 0; extra_layouts && i < (long long)n_extra * n; i++)
+            pos_bound = fmax(pos_bound, fmax(fabs(extra_layouts[i].x), fabs(extra_layouts[i].y)));
+        double rect_bound = 0, rect_height = 0;
+        for (int r = 0; r < n + C; r++) {
+            const int start = r < n ? offlimits[r].point1Index : clearances[r - n].point1Index;
+            double y0 = vertices[start].y, y1 = y0;
+            for (int q = 0; q < 4; q++) {
+                rect_bound = fmax(rect_bound, fmax(fabs(vertices[start + q].x), fabs(vertices[start + q].y)));
+                y0 = fmin(y0, vertices[start + q].y); y1 = fmax(y1, vertices[start + q].y);
+            }
+            rect_height = fmax(rect_height, y1 - y0);
+        }
+        if (!(pos_bound < 1e30) || !(rect_bound < 1e30)) { free(b); set_err("", "non-finite coordinates", 0); return -1; }
+        H.clr_k = clearance_scale(pos_bound, rect_bound, rect_height, n, C);
+        H.clr_scale = (float)ldexp(1.0, H.clr_k);
+        H.clr_unit = (float)ldexp(1.0, -2 * H.clr_k);
+        H.clr_pos_limit = (float)(pos_bound + 1.0);
+    }
+    for (int i = 0; i < n; i++) {
+        const float *fb = b + H.off_obj_box + 4 * i;
+        for (int q = 0; q < 4; q++) bi[H.off_obj_boxq + 4 * i + q] = to_fixed((double)fb[q], (double)H.clr_scale);
+        bi[H.off_obj_v0xq + i] = to_fixed((double)b[H.off_obj_v0x + i], (double)H.clr_scale);
+    }
     for (int i = 0; i < C; i++) {
         rect_consts(vertices, clearances[i].point1Index, b + H.off_clr_box + 4 * i, b + H.off_clr_v0x + i);
+        for (int q = 0; q < 4; q++) bi[H.off_clr_boxq + 4 * i + q] = to_fixed((double)b[H.off_clr_box + 4 * i + q], (double)H.clr_scale);
+        bi[H.off_clr_v0xq + i] = to_fixed((double)b[H.off_clr_v0x + i], (double)H.clr_scale);
         bi[H.off_clr_src + i] = clearances[i].SourceIndex;
         bi[H.off_clr_adj_off + clearances[i].SourceIndex + 1]++;
     }
@@ -289,6 +355,7 @@ struct mhContext {
     uint16_t *d_perm;
     void *d_points, *d_costs, *d_scratch, *d_exch_stats;
     void *h_scratch;   /* 64 bytes of pinned host memory: small read-backs that must not block the host */
+    float *ladder;     /* tempering: the current ladder, rung 0 first (host copy; chains hold a permutation of it) */
     void *stream;
     int own_stream;
     uint64_t it_done;  /* iterations already run (relative to opt.iteration_offset) */
@@ -393,20 +460,22 @@ static int choose_delta_shape(int n, int C, int R, int smem_words, int job_chain
         if (bytes >= 0 && bytes <= max_block) break;
         if (requested > 0) { snprintf(g_err, sizeof g_err, "lanes_per_chain=%d does not fit in shared memory (delta evaluation)", G); return -1; }
     }
-    /* warps per block: whichever of 8 and 4 keeps more warps resident (shared memory; 16 warps per SM is the
-     * register limit at 128 registers), 8 on a tie (the problem blob is staged once per block), and never a
-     * grid smaller than the SM count when 4 would cover it */
+    /* warps per block: whichever of 8, 6 and 4 keeps more warps resident (shared memory; MH_DELTA_REG_WARPS = 16
+     * warps per SM is the register limit at 128 registers), the largest on a tie (the problem blob is staged once
+     * per block), and never a grid smaller than the SM count when a smaller block would cover it */
     int warps = 4, best_res = -1;
     const char *wenv = getenv("MH_DELTA_WARPS");
+    const char *renv = getenv("MH_DELTA_REG_WARPS");
+    const int reg_warps = renv && atoi(renv) > 0 ? atoi(renv) : 16;
     const double total_warps = ceil((double)n_chains * G / 32.0);
-    for (int w = 8; w >= 4; w -= 4) {
+    for (int w = 8; w >= 4; w -= 2) {
         const int bytes = mhdev_chain_smem_bytes(smem_words, n, C, R, G, eval_mode, w);
         if (bytes < 0 || bytes > max_block) continue;
         if (wenv && atoi(wenv) == w) { warps = w; break; }
         int blocks = max_sm / (bytes + 1024);
-        if (blocks * w > 16) blocks = 16 / w;
+        if (blocks * w > reg_warps) blocks = reg_warps / w;
         int res = blocks * w;
-        if (w == 8 && total_warps / w < (double)sms) res = 0;
+        if (w > 4 && total_warps / w < (double)sms) res = 0;
         if (res > best_res) { best_res = res; warps = w; }
     }
     *lanes_out = G;
@@ -420,6 +489,7 @@ static void ctx_free(mhContext *c)
     if (c->n_shards || c->shards) {                            /* multi-device parent: the shards are destroyed by the caller */
         free(c->shards);
         free(c->shard_first);
+        free(c->ladder);
         free(c);
         return;
     }
@@ -429,6 +499,7 @@ static void ctx_free(mhContext *c)
     mhdev_free(c->d_costs, st); mhdev_free(c->d_scratch, st); mhdev_free(c->d_beta_snap, st); mhdev_free(c->d_exch_stats, st);
     for (int i = 0; i < c->n_ev; i++) { mhdev_event_destroy(c->ev[i].e0); mhdev_event_destroy(c->ev[i].e1); }
     free(c->ev);
+    free(c->ladder);
     mhdev_host_free(c->h_scratch);
     if (c->own_stream) mhdev_stream_destroy(c->stream);
     free(c);
@@ -436,18 +507,46 @@ static void ctx_free(mhContext *c)
 
 /* The result block must come from plain malloc() (the reference's callers free() it, Kernel.cu:928),
  * so it cannot be pinned memory.  A fresh 80 MB malloc is untouched address space: copying into it
- * page-faults 20 000 times.  Populate it in one call first (Linux >= 5.14; harmless if unsupported). */
-static void prefault(void *p, size_t bytes)
+ * page-faults 20 000 times.  Populate it first (Linux >= 5.14; harmless if unsupported) -- while the kernel
+ * runs, and on several threads when the block is large: one thread populates about 3 GB/s, the 1.26 GB block of
+ * BASELINE config 4 would take longer than the kernel does on 8 GPUs. */
+typedef struct prefaultJob { void *p; size_t bytes; } prefaultJob;
+
+static void *prefault_worker(void *arg)
 {
 #if defined(__linux__) && defined(MADV_POPULATE_WRITE)
-    if (bytes >= (1u << 20)) {
-        const uintptr_t page = (uintptr_t)sysconf(_SC_PAGESIZE);
-        const uintptr_t a = ((uintptr_t)p + page - 1) & ~(page - 1), e = ((uintptr_t)p + bytes) & ~(page - 1);
-        if (e > a) (void)madvise((void *)a, (size_t)(e - a), MADV_POPULATE_WRITE);
-    }
+    const prefaultJob *j = (const prefaultJob *)arg;
+    const uintptr_t page = (uintptr_t)sysconf(_SC_PAGESIZE);
+    const uintptr_t a = ((uintptr_t)j->p + page - 1) & ~(page - 1), e = ((uintptr_t)j->p + j->bytes) & ~(page - 1);
+    if (e > a) (void)madvise((void *)a, (size_t)(e - a), MADV_POPULATE_WRITE);
 #else
-    (void)p; (void)bytes;
+    (void)arg;
 #endif
+    return NULL;
+}
+
+static void prefault(void *p, size_t bytes)
+{
+    if (bytes < (1u << 20)) return;
+    int threads = (int)(bytes >> 26);                           /* one thread per 64 MB ... */
+    if (threads > 8) threads = 8;                               /* ... at most 8 */
+    if (threads < 1) threads = 1;
+    prefaultJob jobs[8];
+    pthread_t th[8];
+    const size_t slice = ((bytes / (size_t)threads) + 4095) & ~(size_t)4095;
+    int started = 0;
+    for (int i = 0; i < threads; i++) {
+        const size_t off = slice * (size_t)i;
+        if (off >= bytes) { threads = i; break; }
+        jobs[i].p = (char *)p + off;
+        jobs[i].bytes = off + slice <= bytes ? slice : bytes - off;
+    }
+    for (int i = 1; i < threads; i++, started++)
+        if (pthread_create(&th[i], NULL, prefault_worker, &jobs[i])) { prefault_worker(&jobs[i]); th[i] = 0; }
+    prefault_worker(&jobs[0]);
+    for (int i = 1; i < threads; i++)
+        if (th[i]) pthread_join(th[i], NULL);
+    (void)started;
 }
 
 static void default_options(mhOptions *o)
@@ -500,17 +599,25 @@ static int devices_from_env(int32_t devices[MH_MAX_DEVICES])
     return k;
 }
 
-/* rung r of every ladder starts at beta_start * (beta_end/beta_start)^(r/(T-1)) */
+/* rung r of every ladder starts at ladder[r]; the ladder itself starts geometric:
+ * beta_start * (beta_end/beta_start)^(r/(T-1)) */
 static int init_betas(mhContext *c)
 {
     const int T = c->opt.tempering_rungs;
     float *hb = (float *)malloc(4 * (size_t)c->n_chains);
     if (!hb) return 2; /* cudaErrorMemoryAllocation */
-    const float lr = log2f((float)(c->opt.beta_end / c->opt.beta_start));
+    if (!c->ladder) {
+        c->ladder = (float *)malloc(4 * (size_t)T);
+        if (!c->ladder) { free(hb); return 2; }
+        const float lr = log2f((float)(c->opt.beta_end / c->opt.beta_start));
+        for (int r = 0; r < T; r++) {
+            const float t = T > 1 ? (float)r / (float)(T - 1) : 0.f;
+            c->ladder[r] = (float)c->opt.beta_start * exp2f(t * lr);
+        }
+    }
     for (int i = 0; i < c->n_chains; i++) {
         const int r = (int)((c->opt.chain_offset + (uint64_t)i * c->opt.chain_stride) % (uint64_t)T);
-        const float t = T > 1 ? (float)r / (float)(T - 1) : 0.f;
-        hb[i] = (float)c->opt.beta_start * exp2f(t * lr);
+        hb[i] = c->ladder[r];
     }
     int e = mhdev_h2d(c->d_beta, hb, 4 * (size_t)c->n_chains, c->stream);
     if (!e) e = mhdev_stream_sync(c->stream);
@@ -692,7 +799,7 @@ MH_API mhContext *KernelCreate(const relationshipStruct *rss, const relationship
         else if (k == 1) { o.device = o.devices[0]; o.flags |= MH_OPT_EXPLICIT_DEVICE; }
     }
     if (o.n_devices == 1) { o.device = o.devices[0]; o.flags |= MH_OPT_EXPLICIT_DEVICE; o.n_devices = 0; }
-    if (pack_problem(rss, rsa, cfg, clearances, offlimits, vertices, surfaceRectangle, srf, &P)) return NULL;
+    if (pack_problem(rss, rsa, cfg, clearances, offlimits, vertices, surfaceRectangle, srf, NULL, 0, &P)) return NULL;
     mhContext *c = o.n_devices > 1 ? create_multi(&P, nChains, &o) : create_single(&P, nChains, &o);
     free(P.blob);
     return c;
@@ -1312,6 +1419,80 @@ fail:
     return rc;
 }
 
+MH_API int KernelTemperingLadder(mhContext *ctx, double *betas)
+{
+    g_err[0] = 0;
+    if (!ctx || ctx->opt.tempering_rungs <= 1) { set_err("", "context has no tempering ladder", 0); return -1; }
+    const mhContext *src = IS_MULTI(ctx) ? ctx->shards[0] : ctx;
+    for (int r = 0; betas && r < ctx->opt.tempering_rungs; r++) betas[r] = (double)src->ladder[r];
+    return ctx->opt.tempering_rungs;
+}
+
+MH_API int KernelTemperingProposeLadder(int rungs, const double *current, const long long *attempts, const long long *accepted,
+                                        double damping, double *proposed)
+{
+    g_err[0] = 0;
+    if (rungs < 2 || !current || !attempts || !accepted || !proposed || !(damping > 0.0) || damping > 1.0) { set_err("", "bad arguments", 0); return -1; }
+    for (int r = 0; r < rungs; r++)
+        if (!(current[r] > 0.0)) { set_err("", "betas must be positive", 0); return -1; }
+    double *cum = (double *)malloc(sizeof(double) * (size_t)rungs);
+    if (!cum) { set_err("", "out of host memory", 0); return -1; }
+    cum[0] = 0.0;
+    for (int r = 0; r + 1 < rungs; r++) {                       /* the "distance" of every gap */
+        double rate = attempts[r] >= 8 ? (double)accepted[r] / (double)attempts[r] : 0.5;
+        if (rate < 0.01) rate = 0.01;
+        if (rate > 0.99) rate = 0.99;
+        cum[r + 1] = cum[r] - log(rate);
+    }
+    proposed[0] = current[0];
+    proposed[rungs - 1] = current[rungs - 1];
+    int gap = 0;
+    for (int r = 1; r + 1 < rungs; r++) {                       /* rung r at distance r/(T-1) of the total */
+        const double want = cum[rungs - 1] * (double)r / (double)(rungs - 1);
+        while (gap + 2 < rungs && cum[gap + 1] < want) gap++;
+        const double span = cum[gap + 1] - cum[gap];
+        const double f = span > 0 ? (want - cum[gap]) / span : 0.0;
+        const double lb = log(current[gap]) + f * (log(current[gap + 1]) - log(current[gap]));
+        proposed[r] = exp(log(current[r]) + damping * (lb - log(current[r])));
+    }
+    free(cum);
+    return 0;
+}
+
+MH_API int KernelTemperingSetLadder(mhContext *ctx, const double *betas)
+{
+    int prev = -1, rc = -1;
+    void *d_lad = NULL;
+    float *h = NULL;
+    g_err[0] = 0;
+    if (!ctx || ctx->opt.tempering_rungs <= 1 || !betas) { set_err("", "context has no tempering ladder", 0); return -1; }
+    if (IS_MULTI(ctx)) {
+        for (int i = 0; i < ctx->n_shards; i++)
+            if (KernelTemperingSetLadder(ctx->shards[i], betas)) return -1;
+        return 0;
+    }
+    const int T = ctx->opt.tempering_rungs;
+    for (int r = 0; r < T; r++)
+        if (!(betas[r] > 0.0)) { set_err("", "betas must be positive", 0); return -1; }
+    h = (float *)malloc(8 * (size_t)T);
+    if (!h) { set_err("", "out of host memory", 0); return -1; }
+    for (int r = 0; r < T; r++) { h[r] = ctx->ladder[r]; h[T + r] = (float)betas[r]; }
+    CU(enter_device(ctx->device, &prev));
+    CU(mhdev_malloc(&d_lad, 8 * (size_t)T, ctx->stream));
+    CU(mhdev_h2d(d_lad, h, 8 * (size_t)T, ctx->stream));
+    CU(mhdev_launch_retarget(ctx->n_chains, T, (const float *)d_lad, (const float *)d_lad + T, ctx->d_beta, ctx->stream));
+    ctx->launches++;
+    CU(mhdev_memset(ctx->d_exch_stats, 0, 16 * (size_t)T, ctx->stream));
+    CU(mhdev_stream_sync(ctx->stream));                         /* h and d_lad are released below */
+    for (int r = 0; r < T; r++) ctx->ladder[r] = h[T + r];
+    rc = 0;
+fail:
+    if (d_lad) mhdev_free(d_lad, ctx->stream);
+    free(h);
+    if (prev >= 0) leave_device(ctx->device, prev);
+    return rc;
+}
+
 MH_API int KernelStats(mhContext *ctx, double *kernel_ms, long long *launches)
 {
     int prev = -1, rc = -1;
@@ -1479,7 +1660,7 @@ MH_API int KernelEvalCosts(const relationshipStruct *rss, const relationshipAngl
     point *pts = NULL;
     int rc = -1;
     if (nLayouts < 1 || !out || !layouts) { set_err("", "bad arguments", 0); return -1; }
-    if (pack_problem(rss, rsa, layouts, clearances, offlimits, vertices, surfaceRectangle, srf, &P)) return -1;
+    if (pack_problem(rss, rsa, layouts, clearances, offlimits, vertices, surfaceRectangle, srf, layouts, nLayouts, &P)) return -1;
     const int n = P.h->n;
     const size_t cn = (size_t)nLayouts * (size_t)n;
     pts = (point *)calloc(cn, sizeof(point));

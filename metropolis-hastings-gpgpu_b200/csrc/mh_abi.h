@@ -50,6 +50,16 @@ typedef struct mhProblemHeader {
     int32_t off_rel_adj_off; /* int32[n+1] CSR offsets: relationships that name object i (any of the 4 indices) */
     int32_t off_rel_adj;    /* int32[<=4R] CSR list of relationship indices, each at most once per object   */
     int32_t pad3, pad4;
+    /* ClearanceCosts in fixed point (csrc/mh_costs.cuh: "the clearance term is an integer sum"): the AABB
+     * constants above rounded to multiples of 2^-clr_k, positions are rounded the same way on the device */
+    int32_t off_obj_boxq;   /* int4[n]  round(off_obj_box * 2^clr_k)                                   */
+    int32_t off_obj_v0xq;   /* int32[n]                                                                */
+    int32_t off_clr_boxq;   /* int4[C]                                                                 */
+    int32_t off_clr_v0xq;   /* int32[C]                                                                */
+    int32_t clr_k;          /* coordinates are held in units of 2^-clr_k                               */
+    float clr_scale;        /* 2^clr_k                                                                 */
+    float clr_unit;         /* 2^(-2 clr_k): one unit of the integer area sum                          */
+    float clr_pos_limit;    /* positions are clamped to +-this before the conversion (no int32 overflow) */
 } mhProblemHeader;
 
 enum { MH_SCHED_CONSTANT = 0, MH_SCHED_GEOMETRIC = 1, MH_SCHED_LINEAR = 2, MH_SCHED_PER_CHAIN = 3 };
@@ -101,6 +111,8 @@ int mhdev_launch_exchange(int n_chains, uint64_t chain_offset, uint64_t chain_st
                           uint64_t it_last, uint64_t seed, const float *d_all_total, const float *d_all_beta,
                           uint64_t gather_base, uint64_t gather_stride, uint64_t gather_local, float *d_beta,
                           void *d_stats /* uint64[2*rungs] {attempts, accepted} per pair (lower rung), or NULL */, void *stream);
+/* Ladder re-targeting: every chain whose beta is (closest to) old_ladder[r] gets new_ladder[r]; both device float[rungs]. */
+int mhdev_launch_retarget(int n_chains, int rungs, const float *d_old_ladder, const float *d_new_ladder, float *d_beta, void *stream);
 /* Rank keys.  A chain's rank key is the unsigned 64-bit word  orderable(totalCosts) << 32 | (0xFFFFFFFF - chain):
  * an unsigned MAX over keys is the arg-max of totalCosts with ties going to the lower chain index; 0 = "no
  * chain".  (mh_rank_key / mhdev_decode_rank_key) */

@@ -1,4 +1,4 @@
-// mh_delta.cuh -- incremental ("delta") evaluation of a proposal: MH_EVAL_DELTA.
+// mh_delta.cuh -- evaluation of a proposal through memos: MH_EVAL_MEMO (exact) and MH_EVAL_DELTA.
 //
 // A proposal moves one object (translate, rotate) or two (swap).  Full evaluation redoes
 // n^2 + C n pair terms for it; here only what the moved objects touch is recomputed:
@@ -8,17 +8,18 @@
 //              column m of every other row: the row minimum becomes min(old, key(i,m)) unless the
 //              remembered column was m itself, in which case that row is rescanned too.  min is exact,
 //              so the memo always equals what a full evaluation computes -- bit for bit.
-//   clearance  pairs (k, m) for every clearance k, and pairs (k', i) for every clearance k' whose
-//              source object is m: new overlap - old overlap.
+//   clearance  an INTEGER sum (mh_costs.cuh), updated by the pairs the move touches: (k, m) for every
+//              clearance k, and (k', i) for every clearance k' whose source object is m.  Integer addition is
+//              associative, so the updated sum IS the from-scratch sum of the new layout.
 //   surface    the moved objects' own rectangles and the clearances with the same INDEX (quirk Q7).
-//   focal      difference of the memoised cosines;  visual balance: area * displacement.
-//   pair-wise  relationships that name a moved object; their old penalties come from the PR memo.
+//   focal      the memoised cosines;  visual balance: area * position.
+//   pair-wise  relationships that name a moved object; the others come from the PR memo.
 //
-// The additive terms are kept as running sums, so their rounding differs from a full evaluation
-// and drifts; every kRefresh iterations (and at every launch) the memo and the sums are rebuilt
-// from scratch.  Delta mode is therefore statistically, not bitwise, equivalent to full evaluation
-// (tests: KS against the oracle, running total against a fresh evaluation); the costs a caller
-// receives always come from mh_score_kernel, i.e. from a full evaluation of the emitted layout.
+// MH_EVAL_MEMO re-adds the cheap O(n) float sums from their memos in the full evaluation's order, so every
+// total is bit-identical to the plain scan's.  MH_EVAL_DELTA keeps those float sums as running sums instead
+// (new - old), which drift in the last bits and are rebuilt every kRefresh iterations: statistically, not
+// bitwise, equivalent (tests: KS against the oracle, running total against a fresh evaluation).  The costs a
+// caller receives always come from mh_score_kernel, i.e. from a full evaluation of the emitted layout.
 #pragma once
 #include "mh_costs.cuh"
 
@@ -31,33 +32,23 @@ constexpr int kDuClr = 1, kDuRow = 1, kDuScan = 1, kDuSum = 1;
 constexpr int kRefresh = 128; // iterations between full rebuilds of the memo and the running sums
 
 // Which memos a chain keeps (template parameter MODE of mh_delta_kernel):
-//   kModeDelta   MH_EVAL_DELTA: KM + PR, running sums of the additive terms;
-//   kModeExact   MH_EVAL_MEMO : KM + PR + SV, clearance rows from scratch;
-//   kModeExactCR MH_EVAL_MEMO : KM + PR + SV + CR (clearance row sums): used when a warp holds one or two
-//                chains (16 and 32 lanes per chain, rooms of ~100 objects and more: +17 % at n = 100, 1.6x
-//                at n = 200).  With more chains per warp some chain nearly always has many rows to re-add
-//                and the others wait for it (on the dense 50-object room a third of the rows overlaps a
-//                moved clearance): measured slower than re-adding every row, also when the flagged rows of
-//                all chains were dealt to the warp's 32 lanes (ballots + find-nth-set push the code out of
-//                the instruction cache), and also with an 8 x 4 grid of candidate clearances per row
-//                (exact -- zero overlaps do not change a float sum -- but the per-lane candidate lists turn
-//                the broadcast shared-memory loads of the regular loop into scattered ones: 2x slower).
-//                Why so many rows are flagged: the sampler MAXIMISES totalCosts (quirk Q10), with negative
-//                weights that rewards overlap, so the chains pile objects up.  (Re-adding one flagged row per
-//                pass with the whole group -- overlaps side by side, the non-zero ones then added in order
-//                through shuffles -- was 2.3x slower at n = 200 for the same reason: dozens of rows per move.)
-constexpr int kModeDelta = 0, kModeExact = 1, kModeExactCR = 2;
+//   kModeDelta   MH_EVAL_DELTA: KM + PR, running sums of the additive float terms, integer clearance sum;
+//   kModeExact   MH_EVAL_MEMO : KM + PR + SV, float sums re-added from the memos, integer clearance sum.
+// (Round 1 had a third form with a memo of clearance ROW sums for 16- and 32-lane groups -- float sums cannot be
+// updated term by term, so whole rows were re-added whenever one of their overlaps could have changed, and on
+// the piled-up rooms the sampler produces (it MAXIMISES totalCosts, quirk Q10, which rewards overlap) a third of
+// the rows were flagged per move.  The integer sum makes the term itself updatable and the row memo is gone.)
+constexpr int kModeDelta = 0, kModeExact = 1;
 
 template <int G> struct DeltaState {
     static constexpr int CPW = 32 / G;
     float2 *KM; // [2][n][CPW] {row minimum of key, a column attaining it (int bits; -1 = none below 5)}
     float2 *PR; // [R][CPW]    {distance penalty, angle penalty} of every relationship
-    float *SV;  // [n + C][CPW] exact modes: area outside the room of object i's rectangle, then of clearance k's
-    float *CR;  // [2][n][CPW] kModeExactCR: clearance row sums (object i's rectangle against every clearance)
+    float *SV;  // [n + C][CPW] exact mode: area outside the room of object i's rectangle, then of clearance k's
     int n, nC, nR;
     __host__ __device__ static int words(int n, int C, int R, int mode)
     {
-        const int w = CPW * (4 * n + 2 * R + (mode != kModeDelta ? n + C : 0) + (mode == kModeExactCR ? 2 * n : 0));
+        const int w = CPW * (4 * n + 2 * R + (mode != kModeDelta ? n + C : 0));
         return (w + 3) & ~3;                                    // the next warp's float4 state must stay 16-byte aligned
     }
     __device__ __forceinline__ void bind(float *base, int n_, int C, int R)
@@ -68,7 +59,6 @@ template <int G> struct DeltaState {
         KM = reinterpret_cast<float2 *>(base);
         PR = KM + 2 * n * CPW;
         SV = reinterpret_cast<float *>(PR + R * CPW);
-        CR = SV + (n + C) * CPW;
     }
     __device__ __forceinline__ float2 &km(int sel, int i, int c) const
     {
@@ -85,16 +75,12 @@ template <int G> struct DeltaState {
         MH_CHECK(i >= 0 && i < n + nC && c >= 0 && c < CPW);
         return SV[i * CPW + c];
     }
-    __device__ __forceinline__ float &cr(int sel, int i, int c) const
-    {
-        MH_CHECK((sel == 0 || sel == 1) && i >= 0 && i < n && c >= 0 && c < CPW);
-        return CR[(sel * n + i) * CPW + c];
-    }
 };
 
 // Committed running sums of the additive terms (positive magnitudes, as in RawTerms).
 struct RunSums {
-    float pw, pa, vbx, vby, focal, clr, surf;
+    float pw, pa, vbx, vby, focal, surf;
+    long long clr_q;   // the clearance term: an exact integer sum in both modes
 };
 
 // Lexicographic (key, column) minimum over the G lanes of a group.
@@ -271,6 +257,30 @@ __device__ __forceinline__ float sym_rescan_sum(const SmemProblem &P, const Warp
     return group_sum<G, kDeltaStr>(s);
 }
 
+// The clearance sum of the current layout from scratch, WITHOUT the per-warp array of clearance rectangles the
+// plain scan keeps (the memo kernels have no use for it between rebuilds, and its shared memory buys resident
+// warps): every lane walks its rows and rebuilds each clearance rectangle on the fly.  Integer sum: the value is
+// the plain scan's whatever the order.  Runs once per launch (and per refresh in delta mode).
+template <int G>
+__device__ __forceinline__ long long clearance_sum_q(const SmemProblem &P, const float4 *Pc, const int g)
+{
+    constexpr int CPW = 32 / G;
+    const mhProblemHeader *h = P.h;
+    const int n = h->n, C = h->C;
+    long long acc = 0;
+#pragma unroll 1
+    for (int i = g; i < n; i += G) {
+        const float4 pi = Pc[i * CPW];
+        const int4 bi = box_at_q(P.obj_boxq[i], P.obj_v0xq[i], to_fixed(h, pi.x), to_fixed(h, pi.y));
+#pragma unroll 1
+        for (int k = 0; k < C; k++) {
+            const float2 ps = *reinterpret_cast<const float2 *>(&Pc[P.clr_src[k] * CPW]);
+            acc = overlap_add_q(bi, box_at_q(P.clr_boxq[k], P.clr_v0xq[k], to_fixed(h, ps.x), to_fixed(h, ps.y)), acc);
+        }
+    }
+    return group_sum_q<G, kDeltaStr>(acc);
+}
+
 // Rebuild the memo and the running sums of the CURRENT layout from scratch; returns its total.
 template <int G, int MODE>
 __device__ __forceinline__ float delta_rebuild(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, int c, int g, int sel,
@@ -280,27 +290,114 @@ __device__ __forceinline__ float delta_rebuild(const SmemProblem &P, const WarpS
     constexpr int CPW = WS::CPW;
     const mhProblemHeader *h = P.h;
     const int R = h->R;
-    RawTerms t;
-    eval_terms<G, false, kDeltaStr>(P, S, c, g, t); // also refreshes S.CB
-    cur.pw = t.pw; cur.pa = t.pa; cur.vbx = t.vbx; cur.vby = t.vby; cur.focal = t.focal; cur.clr = t.clr; cur.surf = t.surf;
     const float4 *Pc = S.P4 + c;
+    RawTerms t;
+    eval_terms<G, false, kDeltaStr, false, false, true>(P, S, c, g, t);   // every term but the clearance (no S.CB in this kernel)
+    t.clr_q = clearance_sum_q<G>(P, Pc, g);
+    t.clr = clearance_value(h, t.clr_q);
+    cur.pw = t.pw; cur.pa = t.pa; cur.vbx = t.vbx; cur.vby = t.vby; cur.focal = t.focal; cur.clr_q = t.clr_q; cur.surf = t.surf;
     sym_memo_build<G>(P, S, D, c, g, sel);
     for (int r = g; r < R; r += G) {
         float pd, pa;
         rel_pen<CPW>(P, Pc, r, pd, pa);
         D.pr(r, c) = make_float2(pd, pa);
     }
-    if (MODE != kModeDelta) {                                   // surface values; clearance row sums (S.CB is fresh)
+    if (MODE != kModeDelta) {                                   // surface values
         for (int i = g; i < h->n; i += G) {
             const float4 pi = Pc[i * CPW];
-            const float4 bi = box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y);
-            D.sv(i, c) = outside_room(bi, h);
+            D.sv(i, c) = outside_room(box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y), h);
             if (i < h->C) D.sv(h->n + i, c) = outside_room(box_at(P.clr_box[i], P.clr_v0x[i], pi.x, pi.y), h);   // Q7
-            if (MODE == kModeExactCR) D.cr(sel, i, c) = clearance_row<CPW>(bi, S.CB + c, h->C);
         }
     }
     __syncwarp();
     return combine(h, t).total;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Change of the integer clearance sum when object a (and b; -1 = none) moves from oa / ob to na / nb.
+//   part 1 (clearance_delta_moved_rows): the moved objects' own rectangles against EVERY clearance -- a
+//           clearance may itself have moved with its source;
+//   part 2 (inside the callers' pass over the rows): the clearances SOURCED at a moved object against the
+//           rectangles of the objects that did not move.
+// Pc already holds the proposal; the old rectangles are rebuilt from oa / ob.  Returns this lane's share.
+template <int G>
+__device__ __forceinline__ long long clearance_delta_moved_rows(const SmemProblem &P, const float4 *Pc, const int g, const int a, const int b,
+                                                                const bool any_b, const float4 oa, const float4 ob, const float4 na,
+                                                                const float4 nb)
+{
+    constexpr int CPW = 32 / G;
+    const mhProblemHeader *h = P.h;
+    const int C = h->C;
+    const bool mvb = b >= 0;
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+    const int4 ka = P.obj_boxq[a];
+    const int va = P.obj_v0xq[a];
+    const int4 box_oa = box_at_q(ka, va, to_fixed(h, oa.x), to_fixed(h, oa.y));
+    const int4 box_na = box_at_q(ka, va, to_fixed(h, na.x), to_fixed(h, na.y));
+    int4 box_ob = zero4, box_nb = zero4;                        // an empty rectangle: its overlaps are exactly zero
+    if (mvb) {
+        const int4 kb = P.obj_boxq[b];
+        const int vb = P.obj_v0xq[b];
+        box_ob = box_at_q(kb, vb, to_fixed(h, ob.x), to_fixed(h, ob.y));
+        box_nb = box_at_q(kb, vb, to_fixed(h, nb.x), to_fixed(h, nb.y));
+    }
+    long long d = 0;
+#pragma unroll kDuClr
+    for (int k = g; k < C; k += G) {
+        const int src = P.clr_src[k];
+        const float2 pn = *reinterpret_cast<const float2 *>(&Pc[src * CPW]);
+        float2 po = pn;                                         // where the clearance's source was before the move
+        if (src == a) po = make_float2(oa.x, oa.y);
+        if (src == b) po = make_float2(ob.x, ob.y);
+        const int4 kq = P.clr_boxq[k];
+        const int vq = P.clr_v0xq[k];
+        const int4 cb_new = box_at_q(kq, vq, to_fixed(h, pn.x), to_fixed(h, pn.y));
+        const int4 cb_old = box_at_q(kq, vq, to_fixed(h, po.x), to_fixed(h, po.y));
+        d += overlap_q(box_na, cb_new) - overlap_q(box_oa, cb_old);
+        if (any_b) d += overlap_q(box_nb, cb_new) - overlap_q(box_ob, cb_old);
+    }
+    return d;
+}
+
+// The clearances sourced at the moved objects, two per pass (t0, t0 + 1 of the concatenated adjacency lists of a and
+// b): old and new rectangle of each; an absent one is an empty rectangle.
+struct MovedClearances {
+    int4 mo0, mn0, mo1, mn1;
+};
+
+__device__ __forceinline__ MovedClearances moved_clearances(const SmemProblem &P, const int a, const int b, const float4 oa, const float4 ob,
+                                                            const float4 na, const float4 nb, const int t0)
+{
+    const mhProblemHeader *h = P.h;
+    const bool mvb = b >= 0;
+    const int ca0 = P.clr_adj_off[a], na_c = P.clr_adj_off[a + 1] - ca0;
+    const int cb0 = mvb ? P.clr_adj_off[b] : 0, nb_c = mvb ? P.clr_adj_off[b + 1] - cb0 : 0;
+    const int tot = na_c + nb_c;
+    MovedClearances m;
+    m.mo0 = m.mn0 = m.mo1 = m.mn1 = make_int4(0, 0, 0, 0);
+    if (t0 < tot) {
+        const bool fa = t0 < na_c;
+        const int k = P.clr_adj[fa ? ca0 + t0 : cb0 + t0 - na_c];
+        const float4 po = fa ? oa : ob, pn = fa ? na : nb;
+        m.mo0 = box_at_q(P.clr_boxq[k], P.clr_v0xq[k], to_fixed(h, po.x), to_fixed(h, po.y));
+        m.mn0 = box_at_q(P.clr_boxq[k], P.clr_v0xq[k], to_fixed(h, pn.x), to_fixed(h, pn.y));
+    }
+    if (t0 + 1 < tot) {
+        const bool fa = t0 + 1 < na_c;
+        const int k = P.clr_adj[fa ? ca0 + t0 + 1 : cb0 + t0 + 1 - na_c];
+        const float4 po = fa ? oa : ob, pn = fa ? na : nb;
+        m.mo1 = box_at_q(P.clr_boxq[k], P.clr_v0xq[k], to_fixed(h, po.x), to_fixed(h, po.y));
+        m.mn1 = box_at_q(P.clr_boxq[k], P.clr_v0xq[k], to_fixed(h, pn.x), to_fixed(h, pn.y));
+    }
+    return m;
+}
+
+// how many clearances the moved objects carry: this chain's count
+__device__ __forceinline__ int moved_clearance_count(const SmemProblem &P, const int a, const int b)
+{
+    int tot = P.clr_adj_off[a + 1] - P.clr_adj_off[a];
+    if (b >= 0) tot += P.clr_adj_off[b + 1] - P.clr_adj_off[b];
+    return tot;
 }
 
 // Evaluate the proposal that moved object a (and b; -1 = none) from oa/ob to na/nb; S.P4 already
@@ -323,13 +420,13 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
     constexpr unsigned FULL = 0xffffffffu;
     const mhProblemHeader *h = P.h;
     const int n = h->n, C = h->C;
-    const float4 *Pc = S.P4 + c, *CBc = S.CB + c;
+    const float4 *Pc = S.P4 + c;
     const bool mvb = b >= 0;
     const bool any_b = __any_sync(FULL, mvb);
     const float pi_f = 0.5f * h->two_pi;
     MH_CHECK(a >= 0 && a < n && b >= -1 && b < n && b != a && (sel == 0 || sel == 1));
 
-    float d_pw = 0.f, d_pa = 0.f, d_vbx = 0.f, d_vby = 0.f, d_focal = 0.f, d_clr = 0.f, d_surf = 0.f;
+    float d_pw = 0.f, d_pa = 0.f, d_vbx = 0.f, d_vby = 0.f, d_focal = 0.f, d_surf = 0.f;
 
     // ---- the moved objects' own rectangles and the clearances with the same INDEX (quirk Q7), one job per
     //      lane: 0 = object a, 1 = object b, 2 = clearance a, 3 = clearance b --------------------------------
@@ -353,31 +450,8 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
         }
     }
 
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 box_oa, box_na, box_ob = zero4, box_nb = zero4;
-    {
-        const float4 kb = P.obj_box[a];
-        const float v0 = P.obj_v0x[a];
-        box_oa = box_at(kb, v0, oa.x, oa.y);
-        box_na = box_at(kb, v0, na.x, na.y);
-    }
-    if (mvb) {
-        const float4 kb = P.obj_box[b];
-        const float v0 = P.obj_v0x[b];
-        box_ob = box_at(kb, v0, ob.x, ob.y);
-        box_nb = box_at(kb, v0, nb.x, nb.y);
-    }
-
-    // ---- every clearance against the moved objects (the clearance itself may have moved with its source:
-    //      S.P4 already holds the proposal, S.CB still the current layout) ----------------------------------
-#pragma unroll kDuClr
-    for (int k = g; k < C; k += G) {
-        const float4 cb_old = CBc[k * CPW];
-        const float2 ps = *reinterpret_cast<const float2 *>(&Pc[P.clr_src[k] * CPW]);
-        const float4 cb_new = box_at(P.clr_box[k], P.clr_v0x[k], ps.x, ps.y);
-        d_clr += overlap(box_na, cb_new) - overlap(box_oa, cb_old);
-        if (any_b) d_clr += overlap(box_nb, cb_new) - overlap(box_ob, cb_old);
-    }
+    // ---- clearance, part 1: every clearance against the moved objects --------------------------------------------
+    long long d_clr = clearance_delta_moved_rows<G>(P, Pc, g, a, b, any_b, oa, ob, na, nb);
 
     // ---- relationships that name a moved object (CSR by object; one that names both is taken from a's
     //      list only), dealt round-robin to the lanes of the group -------------------------------------------
@@ -415,32 +489,15 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
 
     // ---- one pass over the rows that did not move: (i) symmetry -- column update of the row minimum
     //      (exact: min(old, key(i, a), key(i, b)); a row whose remembered column moved is flagged for a
-    //      rescan); (ii) the row's rectangle against the clearances sourced at a moved object, two such
-    //      clearances per pass (a further pass only if some chain of the warp moved more than two) --------
+    //      rescan); (ii) clearance, part 2: the row's rectangle against the clearances sourced at a moved
+    //      object, two such clearances per pass (a further pass only if some chain of the warp moved more) ------
     unsigned flags = 0;
     {
-        const int ca0 = P.clr_adj_off[a], na_c = P.clr_adj_off[a + 1] - ca0;
-        const int cb0 = mvb ? P.clr_adj_off[b] : 0, nb_c = mvb ? P.clr_adj_off[b + 1] - cb0 : 0;
-        const int tot = na_c + nb_c;
-        const int tmax = __reduce_max_sync(FULL, tot);
+        const int tmax = __reduce_max_sync(FULL, moved_clearance_count(P, a, b));
         const float4 nbx = mvb ? nb : na;
         int t0 = 0;
         do {
-            float4 mo0 = zero4, mn0 = zero4, mo1 = zero4, mn1 = zero4;   // moved clearances: old / new rectangle
-            if (t0 < tot) {
-                const bool fa = t0 < na_c;
-                const int k = P.clr_adj[fa ? ca0 + t0 : cb0 + t0 - na_c];
-                const float4 pm = fa ? na : nb;
-                mo0 = CBc[k * CPW];
-                mn0 = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
-            }
-            if (t0 + 1 < tot) {
-                const bool fa = t0 + 1 < na_c;
-                const int k = P.clr_adj[fa ? ca0 + t0 + 1 : cb0 + t0 + 1 - na_c];
-                const float4 pm = fa ? na : nb;
-                mo1 = CBc[k * CPW];
-                mn1 = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
-            }
+            const MovedClearances mc = moved_clearances(P, a, b, oa, ob, na, nb, t0);
             int p = 0;
 #pragma unroll kDuRow
             for (int i = g; i < n; i += G, p++) {
@@ -449,9 +506,9 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
                 if (t0 == 0 && !moved)                          // (rows a, b are rescanned below)
                     sym_col_update<G>(h, D, c, sel, i, p, pi, a, b, mvb, any_b, na, nbx, pi_f, flags);
                 if (tmax > 0) {
-                    const float4 bi = box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y);
-                    float dd = overlap(bi, mn0) - overlap(bi, mo0);
-                    if (tmax > 1) dd += overlap(bi, mn1) - overlap(bi, mo1);
+                    const int4 bi = box_at_q(P.obj_boxq[i], P.obj_v0xq[i], to_fixed(h, pi.x), to_fixed(h, pi.y));
+                    long long dd = overlap_q(bi, mc.mn0) - overlap_q(bi, mc.mo0);
+                    if (tmax > 1) dd += overlap_q(bi, mc.mn1) - overlap_q(bi, mc.mo1);
                     if (!moved) d_clr += dd;
                 }
             }
@@ -468,17 +525,19 @@ __device__ __forceinline__ float delta_eval(const SmemProblem &P, const WarpStat
     star.vbx = cur.vbx + group_sum<G, kDeltaStr>(d_vbx);
     star.vby = cur.vby + group_sum<G, kDeltaStr>(d_vby);
     star.focal = cur.focal + group_sum<G, kDeltaStr>(d_focal);
-    star.clr = cur.clr + group_sum<G, kDeltaStr>(d_clr);
+    star.clr_q = cur.clr_q + group_sum_q<G, kDeltaStr>(d_clr);
     star.surf = cur.surf + group_sum<G, kDeltaStr>(d_surf);
     RawTerms t;
-    t.pw = star.pw; t.pa = star.pa; t.vbx = star.vbx; t.vby = star.vby; t.focal = star.focal; t.clr = star.clr; t.surf = star.surf;
+    t.pw = star.pw; t.pa = star.pa; t.vbx = star.vbx; t.vby = star.vby; t.focal = star.focal; t.surf = star.surf;
+    t.clr_q = star.clr_q;
+    t.clr = clearance_value(h, star.clr_q);
     t.sym = sym_total;
     t.off = 0.f;
     return combine(h, t).total;
 }
 
-// The proposal was accepted: bring the clearance rectangles and the relationship memo up to the
-// new layout (the KM memo is switched by flipping `sel`).
+// The proposal was accepted: bring the relationship memo up to the new layout (the KM memo is switched by
+// flipping `sel`; the clearance sum travels in RunSums).
 template <int G>
 __device__ __forceinline__ void delta_commit(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, const int c, const int g,
                                              const int a, const int b, const RelStash &stash)
@@ -486,15 +545,6 @@ __device__ __forceinline__ void delta_commit(const SmemProblem &P, const WarpSta
     using WS = WarpState<G>;
     constexpr int CPW = WS::CPW;
     const float4 *Pc = S.P4 + c;
-    for (int which = 0; which < 2; which++) {
-        const int m = which ? b : a;
-        if (m < 0) continue;
-        const float4 pm = Pc[m * CPW];
-        for (int t = P.clr_adj_off[m] + g; t < P.clr_adj_off[m + 1]; t += G) {
-            const int k = P.clr_adj[t];
-            S.CB[WS::at(k, c)] = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
-        }
-    }
     if (stash.r0 >= 0) D.pr(stash.r0, c) = stash.v0;
     if (stash.r1 >= 0) D.pr(stash.r1, c) = stash.v1;
     if (stash.overflow) {                                       // rare: more than 2 G touched relationships
@@ -602,17 +652,15 @@ __device__ __forceinline__ void rel_memo_restore(const SmemProblem &P, const flo
 
 // ---------------------------------------------------------------------------------------------------
 // MH_EVAL_MEMO: full evaluation, bit for bit, at a fraction of the work.  Every term of the proposal is
-// what eval_terms computes for it -- the same values, added in the same order:
-//   symmetry       the exact memo above (row minima; min is exact);
+// what eval_terms computes for it:
+//   symmetry       the exact memo above (row minima; min is exact), summed in eval_terms' order;
 //   relationships  only those that name a moved object are recomputed (into the PR memo); every lane
 //                  then adds ITS relationships r = g, g+G, ... from the memo, as eval_terms does;
 //   surface        per-rectangle values in the SV memo (only the moved objects' change), re-added in
 //                  eval_terms' order: clearances k = g, g+G, ..., then objects i = g, g+G, ...;
 //   visual balance, focal   re-added from the state itself (two FMAs and an add per object);
-//   clearance      every row (object i's rectangle against all clearances, in clearance order) from
-//                  scratch -- or, kModeExactCR, from a memo of the row sums in which only the rows that
-//                  can have changed are re-added.
-// Nothing is a running sum, so nothing drifts and there is no periodic rebuild.
+//   clearance      the integer sum, updated by the pairs the move touches (order-free, hence exact).
+// Nothing is a floating-point running sum, so nothing drifts and there is no periodic rebuild.
 template <int G> struct ExactStash {
     static constexpr int JOBS = (4 + G - 1) / G;   // surface jobs per lane (4 in all: objects a, b, clearances a, b)
     RelMemoStash rel;     // the PR entries this lane overwrote
@@ -629,66 +677,23 @@ __device__ __forceinline__ int sv_slot(const int job, const int a, const int b, 
     return m;
 }
 
-template <int G, int MODE>
+// clr_cur: the integer clearance sum of the current layout; clr_star receives the proposal's.
+template <int G>
 __device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, const int c, const int g,
-                                            const int sel, const int a, const int b, const float4 na, const float4 nb, ExactStash<G> &stash)
+                                            const int sel, const int a, const int b, const float4 oa, const float4 ob, const float4 na,
+                                            const float4 nb, const long long clr_cur, long long &clr_star, ExactStash<G> &stash)
 {
     using WS = WarpState<G>;
     constexpr int CPW = WS::CPW;
     constexpr unsigned FULL = 0xffffffffu;
     const mhProblemHeader *h = P.h;
     const int n = h->n, C = h->C;
-    const float4 *Pc = S.P4 + c, *CBc = S.CB + c;
+    const float4 *Pc = S.P4 + c;
     const bool mvb = b >= 0;
     const bool any_b = __any_sync(FULL, mvb);
     const float pi_f = 0.5f * h->two_pi;
     RawTerms t;
     MH_CHECK(a >= 0 && a < n && b >= -1 && b < n && b != a && (sel == 0 || sel == 1));
-
-    // ---- clearance, step 1 (S.CB still holds the CURRENT layout's rectangles): which rows must be
-    //      re-added?  The moved objects' own rows, and every row whose overlap with a clearance sourced at
-    //      a moved object is non-zero before or after the move.  All other rows keep their sum bit for
-    //      bit: their terms are unchanged except for zeros that stay zeros, and x + 0 = x. -----------------
-    unsigned cflags = 0;
-    if (MODE == kModeExactCR) {
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int ca0 = P.clr_adj_off[a], na_c = P.clr_adj_off[a + 1] - ca0;
-        const int cb0 = mvb ? P.clr_adj_off[b] : 0, nb_c = mvb ? P.clr_adj_off[b + 1] - cb0 : 0;
-        const int tot = na_c + nb_c;
-        const int tmax = __reduce_max_sync(FULL, tot);
-        for (int t0 = 0; t0 < tmax; t0++) {
-            float4 mo = zero4, mn = zero4;                      // the moved clearance before / after
-            if (t0 < tot) {
-                const bool fa = t0 < na_c;
-                const int k = P.clr_adj[fa ? ca0 + t0 : cb0 + t0 - na_c];
-                MH_CHECK(k >= 0 && k < C);
-                const float4 pm = fa ? na : nb;
-                mo = CBc[k * CPW];
-                mn = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
-            }
-            int p = 0;
-#pragma unroll kDuRow
-            for (int i = g; i < n; i += G, p++) {
-                const float4 pi = Pc[i * CPW];
-                const float4 bi = box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y);
-                if (overlap(bi, mo) != 0.f || overlap(bi, mn) != 0.f) cflags |= 1u << p;
-            }
-        }
-        if (a % G == g) cflags |= 1u << (a / G);
-        if (mvb && b % G == g) cflags |= 1u << (b / G);
-        __syncwarp();
-    }
-
-    // ---- the clearance rectangles sourced at a moved object move with it (S.CB := the proposal's) ---------
-    for (int which = 0; which < 2; which++) {
-        const int m = which ? b : a;
-        if (m < 0) continue;
-        const float4 pm = which ? nb : na;
-        for (int tt = P.clr_adj_off[m] + g; tt < P.clr_adj_off[m + 1]; tt += G) {
-            const int k = P.clr_adj[tt];
-            S.CB[WS::at(k, c)] = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
-        }
-    }
 
     // ---- surface values of the moved rectangles, one job per lane -------------------------------------------
 #pragma unroll
@@ -705,90 +710,70 @@ __device__ __forceinline__ float exact_eval(const SmemProblem &P, const WarpStat
         }
     }
 
-    // ---- relationships: memo update and the two sums (synchronises the warp: S.CB and SV, written above,
-    //      are read by other lanes below) -------------------------------------------------------------------
+    // ---- relationships: memo update and the two sums (synchronises the warp: SV, written above, is read by
+    //      other lanes below) -----------------------------------------------------------------------------------
     rel_memo_eval<G, kDeltaStr>(P, Pc, D.PR + c, g, a, b, stash.rel, t.pw, t.pa);
 
-    // ---- clearance ---------------------------------------------------------------------------------------------
-    if (MODE == kModeExactCR) {
-        // re-add the flagged rows (each lane its own, the warp pays for the lane with most), copy the others
-        unsigned todo = cflags;
-        while (__any_sync(FULL, todo != 0)) {
-            const int p = todo ? __ffs(todo) - 1 : 0;
-            const int i = todo ? g + p * G : a;                  // idle lanes shadow row a and drop the result
-            const float4 pi = Pc[i * CPW];
-            const float acc = clearance_row<CPW>(box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y), CBc, C);
-            if (todo) D.cr(1 - sel, i, c) = acc;
-            todo &= todo - 1;
-        }
-    }
-    // ---- one pass over the lane's rows, every sum in eval_terms' order -------------------------------------
+    // ---- clearance, part 1: every clearance against the moved objects ----------------------------------------
+    long long d_clr = clearance_delta_moved_rows<G>(P, Pc, g, a, b, any_b, oa, ob, na, nb);
+
+    // ---- one pass over the lane's rows: the float sums in eval_terms' order; for the rows that did not move the
+    //      symmetry column update and clearance part 2 (the clearances sourced at a moved object) ------------------
+    unsigned flags = 0;
     {
-        float surf = 0.f, clr = 0.f, vbx = 0.f, vby = 0.f, focal = 0.f;
+        float surf = 0.f, vbx = 0.f, vby = 0.f, focal = 0.f;
 #pragma unroll kDuSum
         for (int k = g; k < C; k += G)
             surf += D.sv(n + k, c);
-        int p = 0;
+        const int tmax = __reduce_max_sync(FULL, moved_clearance_count(P, a, b));
+        const float4 nbx = mvb ? nb : na;
+        int t0 = 0;
+        do {
+            const MovedClearances mc = moved_clearances(P, a, b, oa, ob, na, nb, t0);
+            int p = 0;
 #pragma unroll kDuRow
-        for (int i = g; i < n; i += G, p++) {
-            const float4 pi = Pc[i * CPW];
-            const float area = P.obj_area[i];
-            vbx = fmaf(area, pi.x, vbx);
-            vby = fmaf(area, pi.y, vby);
-            focal += pi.w;
-            surf += D.sv(i, c);
-            float acc;
-            if (MODE == kModeExactCR) {
-                if ((cflags >> p) & 1u) {
-                    acc = D.cr(1 - sel, i, c);
-                } else {
-                    acc = D.cr(sel, i, c);
-                    D.cr(1 - sel, i, c) = acc;
+            for (int i = g; i < n; i += G, p++) {
+                const float4 pi = Pc[i * CPW];
+                const bool moved = i == a || i == b;
+                if (t0 == 0) {
+                    const float area = P.obj_area[i];
+                    vbx = fmaf(area, pi.x, vbx);
+                    vby = fmaf(area, pi.y, vby);
+                    focal += pi.w;
+                    surf += D.sv(i, c);
+                    if (!moved) sym_col_update<G>(h, D, c, sel, i, p, pi, a, b, mvb, any_b, na, nbx, pi_f, flags);
                 }
-            } else {
-                acc = clearance_row<CPW>(box_at(P.obj_box[i], P.obj_v0x[i], pi.x, pi.y), CBc, C);
+                if (tmax > 0) {
+                    const int4 bi = box_at_q(P.obj_boxq[i], P.obj_v0xq[i], to_fixed(h, pi.x), to_fixed(h, pi.y));
+                    long long dd = overlap_q(bi, mc.mn0) - overlap_q(bi, mc.mo0);
+                    if (tmax > 1) dd += overlap_q(bi, mc.mn1) - overlap_q(bi, mc.mo1);
+                    if (!moved) d_clr += dd;
+                }
             }
-            clr += acc;
-        }
+            t0 += 2;
+        } while (t0 < tmax);
         t.vbx = group_sum<G, kDeltaStr>(vbx);
         t.vby = group_sum<G, kDeltaStr>(vby);
         t.focal = group_sum<G, kDeltaStr>(focal);
-        t.clr = group_sum<G, kDeltaStr>(clr);
         t.surf = group_sum<G, kDeltaStr>(surf);
         t.off = 0.f;
     }
+    clr_star = clr_cur + group_sum_q<G, kDeltaStr>(d_clr);
+    t.clr_q = clr_star;
+    t.clr = clearance_value(h, clr_star);
 
     // ---- symmetry ------------------------------------------------------------------------------------------------
-    unsigned flags = 0;
-    {
-        const float4 nbx = mvb ? nb : na;
-        int p = 0;
-#pragma unroll kDuRow
-        for (int i = g; i < n; i += G, p++)
-            if (i != a && i != b) sym_col_update<G>(h, D, c, sel, i, p, Pc[i * CPW], a, b, mvb, any_b, na, nbx, pi_f, flags);
-    }
     t.sym = sym_rescan_sum<G>(P, S, D, c, g, sel, a, b, flags);
     return combine(h, t).total;
 }
 
-// The proposal was rejected (S.P4 is restored): put the clearance rectangles, the surface values and the
-// relationship memo back.
+// The proposal was rejected (S.P4 is restored): put the surface values and the relationship memo back.
 template <int G>
 __device__ __forceinline__ void exact_reject(const SmemProblem &P, const WarpState<G> &S, const DeltaState<G> &D, const int c, const int g,
                                              const int a, const int b, const ExactStash<G> &stash)
 {
-    constexpr int CPW = WarpState<G>::CPW;
     const int n = P.h->n, C = P.h->C;
     const float4 *Pc = S.P4 + c;
-    for (int which = 0; which < 2; which++) {
-        const int m = which ? b : a;
-        if (m < 0) continue;
-        const float4 pm = Pc[m * CPW];
-        for (int t = P.clr_adj_off[m] + g; t < P.clr_adj_off[m + 1]; t += G) {
-            const int k = P.clr_adj[t];
-            S.CB[WarpState<G>::at(k, c)] = box_at(P.clr_box[k], P.clr_v0x[k], pm.x, pm.y);
-        }
-    }
 #pragma unroll
     for (int q = 0; q < ExactStash<G>::JOBS; q++) {
         const int job = g + q * G;

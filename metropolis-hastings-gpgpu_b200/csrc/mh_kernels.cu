@@ -30,7 +30,8 @@ namespace mh {
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int THREADS = WARPS_PER_BLOCK * 32;
 #ifndef MH_MIN_BLOCKS
-#define MH_MIN_BLOCKS 5 // resident 128-thread blocks per SM the chain kernel is compiled for (<= 96 registers; 6 blocks = 80 registers measured slower)
+#define MH_MIN_BLOCKS 4 // resident 128-thread blocks per SM the chain kernel is compiled for: <= 128 registers (measured on B200 with the integer
+                        // clearance sum: 4 blocks / 123 registers, no spill, beat 5 blocks / 96 registers (20-byte spill) by 7 % at 8 objects, 12 % at 16, 16 % at 24)
 #endif
 
 struct PointRec {
@@ -70,11 +71,10 @@ __device__ __forceinline__ bool accept_move_fast(float u, float beta, float star
     return accept_move(u, beta, star, cur);
 }
 
-template <int G>
-__device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc, int n, const float *pass, const uint16_t *perm,
+template <class WS>
+__device__ __forceinline__ void write_points_warp(const WS &S, int cc, int n, const float *pass, const uint16_t *perm,
                                                   PointRec *out, int lane)
 {
-    using WS = WarpState<G>;
     float2 *o2 = reinterpret_cast<float2 *>(out);
     for (int q = lane; q < 3 * n; q += 32) {
         const int i = q / 3, part = q - 3 * i;
@@ -94,7 +94,7 @@ __device__ __forceinline__ void write_points_warp(const WarpState<G> &S, int cc,
 template <int G>
 __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const mhLaunch L)
 {
-    using WS = WarpState<G>;
+    using WS = WarpState<G, true>;
     constexpr int CPW = WS::CPW;
     extern __shared__ __align__(16) float smem[];
     const float *gprob = static_cast<const float *>(L.d_problem);
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
             __syncwarp();
             for (int cc = 0; cc < CPW; cc++) {
                 const int ch = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + cc;
-                if (ch < L.n_chains) write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)ch * n, points + (size_t)ch * n, lane);
+                if (ch < L.n_chains) write_points_warp(S, cc, n, pass, L.d_perm + (size_t)ch * n, points + (size_t)ch * n, lane);
             }
         }
     } else {
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
                 for (int cc = 0; cc < CPW; cc++)
                     if (mask & (1u << LM::first_lane(cc))) {
                         const int ch = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + cc;
-                        write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)ch * n, points + (size_t)ch * n, lane);
+                        write_points_warp(S, cc, n, pass, L.d_perm + (size_t)ch * n, points + (size_t)ch * n, lane);
                     }
             }
         }
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
     if (L.result_mode == 0) {                                  // Kernel.cu:834-842: the final current layout
         for (int cc = 0; cc < CPW; cc++) {
             const int ch = (blockIdx.x * WARPS_PER_BLOCK + warp) * CPW + cc;
-            if (ch < L.n_chains) write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)ch * n, points + (size_t)ch * n, lane);
+            if (ch < L.n_chains) write_points_warp(S, cc, n, pass, L.d_perm + (size_t)ch * n, points + (size_t)ch * n, lane);
         }
     }
 }
@@ -303,11 +303,18 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
 //  * no branch on the move type: translate / rotate / swap are computed side by side and selected,
 //    so the chains of a warp do not serialise;
 //  * the two Philox blocks of an iteration are computed by different lanes of the group at once.
-// MODE = kModeDelta: MH_EVAL_DELTA (delta_eval: running sums, statistically equivalent to full evaluation);
-// MODE = kModeExact / kModeExactCR: MH_EVAL_MEMO (exact_eval: every total bit-identical to the full
-// evaluation's), without / with the memo of the clearance row sums.
+// MODE = kModeDelta: MH_EVAL_DELTA (delta_eval: running float sums, statistically equivalent to full evaluation);
+// MODE = kModeExact: MH_EVAL_MEMO (exact_eval: every total bit-identical to the full evaluation's).
+// Neither keeps the plain scan's per-warp array of clearance rectangles: the clearance term is an integer sum
+// updated pair by pair (mh_costs.cuh), the old rectangles are rebuilt from the moved objects' old positions.
+#ifndef MH_DELTA_THREADS
+#define MH_DELTA_THREADS 256   // largest block of the memo kernels (8 warps) ...
+#endif
+#ifndef MH_DELTA_MIN_BLOCKS
+#define MH_DELTA_MIN_BLOCKS 2  // ... and the resident blocks per SM they are compiled for: 128 registers per thread
+#endif
 template <int G, int MODE>
-__global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
+__global__ void __launch_bounds__(MH_DELTA_THREADS, MH_DELTA_MIN_BLOCKS) mh_delta_kernel(const mhLaunch L)
 {
     using WS = WarpState<G>;
     using DS = DeltaState<G>;
@@ -327,9 +334,9 @@ __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
     WS S;
     DS D;
     {
-        float *base = smem + L.smem_words + warp * (WS::words(n, C) + DS::words(n, C, h->R, MODE));
-        S.bind(base, n, C);
-        D.bind(base + WS::words(n, C), n, C, h->R);
+        float *base = smem + L.smem_words + warp * (WS::words(n, 0) + DS::words(n, C, h->R, MODE));
+        S.bind(base, n, 0);                                     // no clearance-rectangle array in this kernel
+        D.bind(base + WS::words(n, 0), n, C, h->R);
     }
     const int chain0 = (blockIdx.x * warps + warp) * CPW;     // first chain of this warp
     const bool live = chain0 + c < L.n_chains;
@@ -359,7 +366,7 @@ __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
     if (L.fresh && L.result_mode == 1) {
         for (int cc = 0; cc < CPW; cc++)
             if (chain0 + cc < L.n_chains)
-                write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)(chain0 + cc) * n, points + (size_t)(chain0 + cc) * n, lane);
+                write_points_warp(S, cc, n, pass, L.d_perm + (size_t)(chain0 + cc) * n, points + (size_t)(chain0 + cc) * n, lane);
     }
 
     const float room_x0 = h->room_minx, room_y0 = h->room_miny, room_x1 = h->room_maxx, room_y1 = h->room_maxy;
@@ -443,7 +450,7 @@ __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
         RelStash stash;
         ExactStash<G> xstash;
         float star;
-        if (EXACT) star = exact_eval<G, MODE>(P, S, D, c, g, sel, a_e, b_eff, na, nb, xstash);
+        if (EXACT) star = exact_eval<G>(P, S, D, c, g, sel, a_e, b_eff, oa, ob, na, nb, sums.clr_q, star_sums.clr_q, xstash);
         else star = delta_eval<G>(P, S, D, c, g, sel, a_e, b_eff, oa, ob, na, nb, sums, star_sums, stash);
 
         // -- accept (Kernel.cu:706-713) -------------------------------------------------------------------
@@ -452,7 +459,9 @@ __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
         if (acc) {
             cur = star;
             sel ^= 1;
-            if (!EXACT) {
+            if (EXACT) {
+                sums.clr_q = star_sums.clr_q;
+            } else {
                 sums = star_sums;
                 delta_commit<G>(P, S, D, c, g, a_e, b_eff, stash);
             }
@@ -475,7 +484,7 @@ __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
             if (mask) {
                 for (int cc = 0; cc < CPW; cc++)
                     if (mask & (1u << LM::first_lane(cc)))
-                        write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)(chain0 + cc) * n, points + (size_t)(chain0 + cc) * n, lane);
+                        write_points_warp(S, cc, n, pass, L.d_perm + (size_t)(chain0 + cc) * n, points + (size_t)(chain0 + cc) * n, lane);
             }
         }
         if (trace && live && g == 0) {
@@ -503,7 +512,7 @@ __global__ void __launch_bounds__(256, 2) mh_delta_kernel(const mhLaunch L)
     if (L.result_mode == 0) {
         for (int cc = 0; cc < CPW; cc++)
             if (chain0 + cc < L.n_chains)
-                write_points_warp<G>(S, cc, n, pass, L.d_perm + (size_t)(chain0 + cc) * n, points + (size_t)(chain0 + cc) * n, lane);
+                write_points_warp(S, cc, n, pass, L.d_perm + (size_t)(chain0 + cc) * n, points + (size_t)(chain0 + cc) * n, lane);
     }
 }
 
@@ -512,7 +521,7 @@ template <int G>
 __global__ void __launch_bounds__(THREADS) mh_score_kernel(const float *__restrict__ gprob, int smem_words, int n_layouts,
                                                            const PointRec *__restrict__ points, Costs8 *__restrict__ costs)
 {
-    using WS = WarpState<G>;
+    using WS = WarpState<G, true>;
     constexpr int CPW = WS::CPW;
     extern __shared__ __align__(16) float smem[];
     stage_problem(smem, gprob, smem_words);
@@ -565,6 +574,22 @@ __global__ void mh_exchange_kernel(int n_chains, uint64_t chain_offset, uint64_t
         atomicAdd(&stats[2 * lo_r], 1ull);
         if (u < pacc) atomicAdd(&stats[2 * lo_r + 1], 1ull);
     }
+}
+
+// Ladder tuning (KernelTemperingSetLadder): a chain sitting on rung r of the old ladder moves to rung r of the new one.
+__global__ void mh_retarget_kernel(int n_chains, int rungs, const float *__restrict__ old_ladder, const float *__restrict__ new_ladder,
+                                   float *__restrict__ beta)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chains) return;
+    const float b = beta[i];
+    int best = 0;
+    float bd = fabsf(b - old_ladder[0]);
+    for (int r = 1; r < rungs; r++) {
+        const float d = fabsf(b - old_ladder[r]);
+        if (d < bd) { bd = d; best = r; }
+    }
+    beta[i] = new_ladder[best];
 }
 
 // ---- ranking on the device -----------------------------------------------------------------------------
@@ -705,7 +730,7 @@ __global__ void mh_bestkey_kernel(const unsigned long long *__restrict__ rank, u
 
 template <int G> static int launch_scan_g(const mhLaunch &L)
 {
-    using WS = WarpState<G>;
+    using WS = WarpState<G, true>;
     const int chains_per_block = WARPS_PER_BLOCK * WS::CPW;
     const int blocks = (L.n_chains + chains_per_block - 1) / chains_per_block;
     const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)WARPS_PER_BLOCK * WS::words(L.n, L.C));
@@ -715,16 +740,13 @@ template <int G> static int launch_scan_g(const mhLaunch &L)
     return (int)cudaGetLastError();
 }
 
-// the memo form keeps clearance row sums only when a warp holds one or two chains (mh_delta.cuh)
-constexpr int exact_mode(int G) { return G >= 16 ? kModeExactCR : kModeExact; }
-
 template <int G, int MODE> static int launch_delta_g(const mhLaunch &L)
 {
     using WS = WarpState<G>;
-    const int warps = L.warps_per_block == 8 ? 8 : 4;
+    const int warps = L.warps_per_block >= 1 && L.warps_per_block <= MH_DELTA_THREADS / 32 ? L.warps_per_block : 4;
     const int chains_per_block = warps * WS::CPW;
     const int blocks = (L.n_chains + chains_per_block - 1) / chains_per_block;
-    const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)warps * (WS::words(L.n, L.C) + DeltaState<G>::words(L.n, L.C, L.R, MODE)));
+    const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)warps * (WS::words(L.n, 0) + DeltaState<G>::words(L.n, L.C, L.R, MODE)));
     cudaError_t e = cudaFuncSetAttribute(mh_delta_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     mh_delta_kernel<G, MODE><<<blocks, warps * 32, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
@@ -735,7 +757,7 @@ template <int G> static int launch_chains_g(const mhLaunch &L)
 {
     switch (L.eval_mode) {
     case 1: return launch_delta_g<G, kModeDelta>(L);
-    case 2: return launch_delta_g<G, exact_mode(G)>(L);
+    case 2: return launch_delta_g<G, kModeExact>(L);
     default: return launch_scan_g<G>(L);
     }
 }
@@ -744,7 +766,7 @@ template <int G>
 static int launch_score_g(const void *d_problem, int smem_words, int n, int C, int n_layouts, const void *d_points, void *d_costs,
                           void *stream)
 {
-    using WS = WarpState<G>;
+    using WS = WarpState<G, true>;
     const int per_block = WARPS_PER_BLOCK * WS::CPW;
     const int blocks = (n_layouts + per_block - 1) / per_block;
     const size_t smem = sizeof(float) * ((size_t)smem_words + (size_t)WARPS_PER_BLOCK * WS::words(n, C));
@@ -758,8 +780,9 @@ static int launch_score_g(const void *d_problem, int smem_words, int n, int C, i
 
 template <int G> static int chain_words(int n, int C, int R, int eval_mode)
 {
-    const int dm = eval_mode == 1 ? kModeDelta : exact_mode(G);
-    return WarpState<G>::words(n, C) + (eval_mode == 1 || eval_mode == 2 ? DeltaState<G>::words(n, C, R, dm) : 0);
+    if (eval_mode == 1 || eval_mode == 2)                       // the memo kernels keep no clearance-rectangle array
+        return WarpState<G>::words(n, 0) + DeltaState<G>::words(n, C, R, eval_mode == 1 ? kModeDelta : kModeExact);
+    return WarpState<G, true>::words(n, C);
 }
 
 } // namespace mh
@@ -780,7 +803,7 @@ int mhdev_chain_smem_bytes(int smem_words, int n, int C, int R, int lanes, int e
     default: return -1;
     }
     if (memo && (n + lanes - 1) / lanes > 32) return -1; /* the per-lane row flags are one 32-bit word */
-    if (!memo || warps != 8) warps = mh::WARPS_PER_BLOCK;
+    if (!memo || warps < 1 || warps > MH_DELTA_THREADS / 32) warps = mh::WARPS_PER_BLOCK;
     return 4 * (smem_words + warps * w);
 }
 
@@ -822,6 +845,13 @@ int mhdev_launch_exchange(int n_chains, uint64_t chain_offset, uint64_t chain_st
     mh::mh_exchange_kernel<<<(n_chains + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         n_chains, chain_offset, chain_stride, rungs, epoch, it_last, seed, d_all_total, d_all_beta, gather_base, gather_stride,
         gather_local, d_beta, static_cast<unsigned long long *>(d_stats));
+    return (int)cudaGetLastError();
+}
+
+int mhdev_launch_retarget(int n_chains, int rungs, const float *d_old_ladder, const float *d_new_ladder, float *d_beta, void *stream)
+{
+    if (n_chains <= 0) return 0;
+    mh::mh_retarget_kernel<<<(n_chains + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(n_chains, rungs, d_old_ladder, d_new_ladder, d_beta);
     return (int)cudaGetLastError();
 }
 

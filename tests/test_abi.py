@@ -81,6 +81,36 @@ def test_options_struct_grows_compatibly():
     assert int(pkg.binding.make_options()["device"][0]) == -1
 
 
+def test_ladder_policy_is_a_pure_host_function():
+    """KernelTemperingProposeLadder needs no device: end points stay, the ladder stays monotone, equal exchange rates
+    leave it alone, rungs move towards the gaps that exchange least, and on a synthetic model of the exchange rate
+    (acceptance = exp(-c(beta) * gap in log beta), harder towards the cold end) iterating it equalises the rates."""
+    k = pkg.Kernel()
+    cur = 0.25 * 32.0 ** (np.arange(8) / 7)
+    att = np.full(7, 1000)
+    same = k.propose_ladder(cur, att, np.full(7, 400))
+    assert np.allclose(same, cur, rtol=1e-12)
+    new = k.propose_ladder(cur, att, np.array([900, 800, 600, 300, 100, 20, 5]))
+    assert new[0] == cur[0] and new[-1] == cur[-1] and np.all(np.diff(new) > 0)
+    assert np.all(new[1:-1] > cur[1:-1])                        # the cold end exchanges least: rungs move there
+    half = k.propose_ladder(cur, att, np.array([900, 800, 600, 300, 100, 20, 5]), damping=0.5)
+    assert np.allclose(np.log(half), 0.5 * (np.log(cur) + np.log(new)))
+    few = k.propose_ladder(cur, np.full(7, 3), np.zeros(7, np.int64))    # too few attempts to say anything
+    assert np.allclose(few, cur, rtol=1e-12)
+
+    def rates(lad):
+        mid = np.sqrt(lad[1:] * lad[:-1])
+        return np.exp(-(0.3 + 0.5 * mid) * np.diff(np.log(lad)))
+    lad = cur.copy()
+    for _ in range(30):
+        r = rates(lad)
+        lad = k.propose_ladder(lad, np.full(7, 100000), np.round(r * 100000).astype(np.int64), damping=0.7)
+    r = rates(lad)
+    assert r.max() / r.min() < 1.15 and rates(cur).max() / rates(cur).min() > 3
+    with pytest.raises(pkg.KernelError):
+        k.propose_ladder([1.0, -2.0], [1], [1])
+
+
 def test_oracle_is_not_linked_into_the_product():
     """Nothing under oracle/ may be included, linked or loaded by the product (comments may say the word)."""
     out = subprocess.run(["nm", "-D", pkg.lib_path()], capture_output=True, text=True, check=True).stdout

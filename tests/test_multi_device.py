@@ -194,3 +194,34 @@ def test_a_failed_launch_leaves_the_context_usable(kernel, monkeypatch):
         ref.run(50)
         assert ctx.results()[0].tobytes() == ref.results()[0].tobytes()
         assert ctx.stats()[1] == ref.stats()[1]
+
+
+def test_ladder_tuning_retargets_the_chains(kernel):
+    """KernelTemperingLadder / ProposeLadder / SetLadder: after a re-target every ladder still holds a permutation of
+    its rungs -- the NEW rungs; the statistics restart; multi-device contexts follow; KernelReset restarts the chains
+    on the tuned ladder."""
+    room = S.make_config(2)
+    rungs, ex = 6, 10
+    opts = dict(seed=3, beta_start=0.25, beta_end=8.0, tempering_rungs=rungs, exchange_interval=ex)
+    for devs in (None, [0, 0, 0]):
+        with kernel.create(room, rungs * 50, devices=devs, **opts) as ctx:
+            geo = 0.25 * 32.0 ** (np.arange(rungs) / (rungs - 1))
+            np.testing.assert_allclose(ctx.ladder(rungs), geo, rtol=1e-6)
+            ctx.run(20 * ex)
+            att, acc = ctx.tempering_stats(rungs)
+            assert att.sum() > 0
+            new = kernel.propose_ladder(ctx.ladder(rungs), att, acc, damping=1.0)
+            assert new[0] == pytest.approx(0.25) and new[-1] == pytest.approx(8.0) and np.all(np.diff(new) > 0)
+            ctx.set_ladder(new)
+            np.testing.assert_allclose(ctx.ladder(rungs), new, rtol=1e-6)
+            att2, acc2 = ctx.tempering_stats(rungs)
+            assert att2.sum() == 0 and acc2.sum() == 0
+            tr = ctx.run_traced(3 * ex)
+            got = np.sort(tr["beta"][-1].reshape(50, rungs), axis=1)
+            np.testing.assert_allclose(got, np.tile(np.float32(new), (50, 1)), rtol=1e-6)
+            ctx.reset()
+            tr = ctx.run_traced(1)
+            np.testing.assert_allclose(tr["beta"][0].reshape(50, rungs), np.tile(np.float32(new), (50, 1)), rtol=1e-6)
+    with kernel.create(room, 8, seed=1) as plain:
+        with pytest.raises(pkg.KernelError, match="ladder"):
+            plain.ladder(4)

@@ -1,28 +1,21 @@
-"""Development probe: where does the time of a KernelWrapperEx call go."""
+"""Development probe: where does the time of a KernelWrapperEx call go (MH_TIMING=1 prints the library's own phases).
+usage: e2e_probe.py [config id] [chains] [iterations]   (env MH_PIN_RESULT=1: page-lock the result block for the copy)"""
 import importlib, os, sys, time
-import ctypes as C
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (tools/ sits one level below)
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("metropolis-hastings-gpgpu_b200")
-from importlib import import_module
-B = import_module("metropolis-hastings-gpgpu_b200.binding")
-k = pkg.Kernel(); room = pkg.synth.make_config(3); L = pkg.layout
-chains, iters = 65536, 1000
+cid = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+chains = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
+k = pkg.Kernel(); room = pkg.synth.make_config(cid)
 k.wrapper_ex(room, 1024, 10, seed=1)
-for rep in range(5):
-    g = np.zeros(1, L.gpuConfig); g["gridxDim"], g["blockxDim"], g["iterations"] = chains, 64, iters
-    o = B.make_options(seed=3)
+print(f"config {cid}, {chains} chains x {iters} iterations, result block {chains * room.n * 24 / 1e6:.0f} MB, MH_PIN_RESULT={os.environ.get('MH_PIN_RESULT', '')}")
+for rep in range(3):
     t0 = time.perf_counter()
-    res = k.lib.KernelWrapperEx(*k._room_args(room), B._ptr(g), B._ptr(o))
+    res, pts, costs = k.wrapper_ex_raw(room, chains, iters, seed=3)
     t1 = time.perf_counter()
-    pts, costs = k._unpack(res, chains, room.n)
+    best = float(costs["totalCosts"].max())
+    k.free(res)
     t2 = time.perf_counter()
-    print(f"KernelWrapperEx {1e3*(t1-t0):.1f} ms, python unpack+free {1e3*(t2-t1):.1f} ms")
-    t0 = time.perf_counter()
-    ctx = k.create(room, chains, seed=3); t1 = time.perf_counter()
-    ctx.run(iters); ctx.synchronize(); t2 = time.perf_counter()
-    p, c = ctx.results(); t3 = time.perf_counter()
-    ms, _ = ctx.stats()
-    ctx.close(); t4 = time.perf_counter()
-    print(f"  create {1e3*(t1-t0):.1f} run {1e3*(t2-t1):.1f} (kernel {ms:.1f}) results {1e3*(t3-t2):.1f} destroy {1e3*(t4-t3):.1f} ms")
+    print(f"KernelWrapperEx {1e3*(t1-t0):.1f} ms, read + free {1e3*(t2-t1):.1f} ms")

@@ -54,7 +54,7 @@ def main():
             big = np.abs(r) > 0.1 * sc[f]
             rel = np.abs(g[big] - r[big]) / np.abs(r[big]) if big.any() else np.zeros(0)
             small = np.abs(g[~big] - r[~big]) / sc[f] if (~big).any() else np.zeros(0)
-            terms[f] = {"scale": sc[f], "n_rel": int(big.sum()), "rel_worst": float(rel.max()) if len(rel) else None,
+            terms[f] = {"scale": float(sc[f]), "n_rel": int(big.sum()), "rel_worst": float(rel.max()) if len(rel) else None,
                         "rel_p999": float(np.quantile(rel, 0.999)) if len(rel) else None,
                         "rel_median": float(np.median(rel)) if len(rel) else None,
                         "n_small": int((~big).sum()), "abs_over_scale_worst": float(small.max()) if len(small) else None,
