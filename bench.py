@@ -506,7 +506,7 @@ def c_abi_multi_gpu(pl, k, pkg, steps):
     return out
 
 
-def config2_as_named(k, pkg):
+def config2_as_named(k, pkg, with_reference=True):
     """BASELINE config 2 exactly as named: the 16-object bedroom, 1024 chains x 10000 iterations on one B200 (an
     under-filled machine: 1024 chains are 7 warps per SM at the default lane width), beside the reference kernel
     rebuilt for sm_100 on the SAME workload."""
@@ -531,7 +531,7 @@ def config2_as_named(k, pkg):
     out = {"workload": f"config 2 ({room.name}): n={room.n} C={room.C} R={room.R}, {chains} chains x {iters} iterations", "unit": UNIT,
            "kernel_only": chains * iters / ((ms1 - ms0) * 1e-3), "e2e": e2e, "lanes_per_chain": shape["lanes_per_chain"]}
     try:
-        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libKernel_ref_nb.so")):
+        if with_reference and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libKernel_ref_nb.so")):
             v_wall, v_dev, _ = reference_gpu(2, chains, iters, 1, 1, timeout_s=120)
             r = reference_gpu.last
             out["ref_gpu_baseline"] = {"value": v_wall, "unit": UNIT, "device_events": v_dev, "without_init_rng": r.get("proposals_per_s_dev_without_init_rng"),
@@ -686,7 +686,7 @@ def main():
                 "best": {"global_chain": int(best[0]), "totalCosts": float(best[1])}, "device": info["name"]}
         line.update(extras)
         if not args.no_extras and world == 1:                    # the side measurements run at N=1 only
-            line["config2_as_named"] = config2_as_named(k, pkg)
+            line["config2_as_named"] = config2_as_named(k, pkg, with_reference=not args.no_ref_gpu)
             line["other_configs_kernel_only"] = other_configs(k, pkg)
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_baseline(room)

@@ -28,7 +28,19 @@ namespace mh {
 // The loops of delta_eval are deliberately NOT unrolled: the kernel's per-iteration code path must stay
 // inside the 32 KB instruction cache (measured at n = 50: 8.4e8 proposals/s rolled against 7.2e8 with
 // the compiler's 4x unrolling -- with the unrolled code the warps of an SM evict each other's lines).
-constexpr int kDuClr = 1, kDuRow = 1, kDuScan = 1, kDuSum = 1;
+#ifndef MH_DU_CLR
+#define MH_DU_CLR 1
+#endif
+#ifndef MH_DU_ROW
+#define MH_DU_ROW 1
+#endif
+#ifndef MH_DU_SCAN
+#define MH_DU_SCAN 1
+#endif
+#ifndef MH_DU_SUM
+#define MH_DU_SUM 1
+#endif
+constexpr int kDuClr = MH_DU_CLR, kDuRow = MH_DU_ROW, kDuScan = MH_DU_SCAN, kDuSum = MH_DU_SUM;
 constexpr int kRefresh = 128; // iterations between full rebuilds of the memo and the running sums
 
 // Which memos a chain keeps (template parameter MODE of mh_delta_kernel):

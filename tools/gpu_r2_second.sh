@@ -21,6 +21,10 @@ for t in "r2a_memo_n50_g8 3 65536 200 8 0" "r2b_scan_n16 2 65536 300 0 0" "r2c_m
   set -- $t; name=$1; shift
   python tools/prof_target.py "$@" > gpurun_out/${name}_clean.log 2>&1 || continue
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mh_chain|mh_delta" -s 1 -c 1 -f -o gpurun_out/prof_${name} python tools/prof_target.py "$@" > gpurun_out/${name}_ncu.log 2>&1
+  # gpurun brings back at most 64 MiB: condense on the box, keep only the first capture's .ncu-rep
+  python tools/ncu_summary.py gpurun_out/prof_${name}.ncu-rep > gpurun_out/${name}_ncu_full.txt 2>> gpurun_out/${name}_ncu.log
+  ncu -i gpurun_out/prof_${name}.ncu-rep --page source --csv 2>/dev/null | gzip -9 > gpurun_out/${name}_source.csv.gz
+  [ "$name" = r2a_memo_n50_g8 ] || rm -f gpurun_out/prof_${name}.ncu-rep
 done
 python bench.py --steps 2 --warmup 3 --iterations 200 --no-cpu-baseline --no-ref-gpu > gpurun_out/r2b_bench_iters200.json 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches_bench_iters200.csv python bench.py --steps 2 --warmup 3 --iterations 200 --no-cpu-baseline --no-ref-gpu > gpurun_out/r2b_ncu_bench.log 2>&1
