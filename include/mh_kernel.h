@@ -212,9 +212,10 @@ MH_API int KernelTopK(mhContext *ctx, int k, int *chains, float *totals);
  * layout is farther than minDistance from every chain taken before it.  The distance of two layouts is the
  * largest displacement of any object: max_i max(|dx_i|, |dy_i|, rotWeight * |drotY_i| wrapped into
  * [0, 3.1416]); rotWeight = 0 ignores rotations.  Distances and the masked arg-max run on the device
- * (k rounds of two small kernels); many chains of a converged run are near-duplicates, and the caller
- * wants a handful of different rooms to show.  Returns how many were written (<= k; fewer when everything
- * left is a near-duplicate) or -1. */
+ * (one fused kernel per pick, all k enqueued at once, one read-back; on a multi-device context one small host
+ * round trip per pick hands the pick's layout to the other devices); many chains of a converged run are
+ * near-duplicates, and the caller wants a handful of different rooms to show.  Returns how many were written
+ * (<= k; fewer when everything left is a near-duplicate) or -1. */
 MH_API int KernelTopKDistinct(mhContext *ctx, int k, float minDistance, float rotWeight, int *chains, float *totals);
 /* Multi-GPU arg-best: writes to the DEVICE address d_key one signed 64-bit key that orders like
  * (totalCosts of this context's best chain, lower global chain id first).  A MAX all-reduce of

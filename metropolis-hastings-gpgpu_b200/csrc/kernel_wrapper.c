@@ -1257,6 +1257,90 @@ MH_API int KernelTopK(mhContext *ctx, int k, int *chains, float *totals)
     return k;
 }
 
+/* KernelTopKDistinct on a context spread over several devices.  Every round each device runs the fused round kernel on
+ * its own chains (distance to the previous pick, masked arg-max), the host compares the <= 8 candidate keys, reads the
+ * winner's layout (n x 24 bytes) from its device and hands it to every device as the next round's reference.  One small
+ * host round trip per pick instead of none -- the price of the layouts living on different devices. */
+typedef struct distinctShard { float *d_mind; void *d_keys, *d_ref; } distinctShard;
+
+static int topk_distinct_multi(mhContext *ctx, int k, float minDistance, float rotWeight, int *chains, float *totals)
+{
+    const int S = ctx->n_shards, n = ctx->n;
+    int rc = -1, found = 0, prev = -1;
+    distinctShard *ds = (distinctShard *)calloc((size_t)S, sizeof *ds);
+    point *ref = (point *)malloc(sizeof(point) * (size_t)n);
+    if (!ds || !ref) { set_err("", "out of host memory", 0); goto done; }
+    for (int i = 0; i < S; i++) {
+        mhContext *c = ctx->shards[i];
+        prev = -1;
+        CU(enter_device(c->device, &prev));
+        CU(ensure_scored(c));
+        CU(mhdev_malloc((void **)&ds[i].d_mind, sizeof(float) * (size_t)c->n_chains, c->stream));
+        CU(mhdev_malloc(&ds[i].d_keys, 8 * (size_t)k, c->stream));
+        CU(mhdev_malloc(&ds[i].d_ref, sizeof(point) * (size_t)n, c->stream));
+        CU(mhdev_memset(ds[i].d_keys, 0, 8 * (size_t)k, c->stream));
+        leave_device(c->device, prev);
+        prev = -1;
+    }
+    for (found = 0; found < k; found++) {
+        for (int i = 0; i < S; i++) {                           /* every device works on the round at the same time */
+            mhContext *c = ctx->shards[i];
+            prev = -1;
+            CU(enter_device(c->device, &prev));
+            CU(mhdev_launch_distinct_round(c->d_costs, c->d_points, n, c->n_chains, found, minDistance, rotWeight, (float)(2 * MH_PI),
+                                           ds[i].d_mind, ds[i].d_keys, found ? ds[i].d_ref : NULL, c->stream));
+            c->launches++;
+            CU(mhdev_d2h(c->h_scratch, (const char *)ds[i].d_keys + 8 * (size_t)found, 8, c->stream));
+            leave_device(c->device, prev);
+            prev = -1;
+        }
+        int best_shard = -1, best_idx = -1;
+        float best_total = 0.f;
+        for (int i = 0; i < S; i++) {
+            if (KernelSynchronize(ctx->shards[i])) goto done;
+            float t = 0.f;
+            const int idx = decode_rank_key(*(const uint64_t *)ctx->shards[i]->h_scratch, &t);
+            if (idx >= 0 && (best_shard < 0 || t > best_total)) { best_shard = i; best_idx = idx; best_total = t; }
+        }
+        if (best_shard < 0) break;                              /* every remaining chain is a near-duplicate */
+        if (chains) chains[found] = ctx->shard_first[best_shard] + best_idx;
+        if (totals) totals[found] = best_total;
+        if (found + 1 < k) {                                    /* the pick's layout becomes every device's next reference */
+            mhContext *w = ctx->shards[best_shard];
+            prev = -1;
+            CU(enter_device(w->device, &prev));
+            CU(mhdev_d2h(ref, (const char *)w->d_points + sizeof(point) * (size_t)best_idx * (size_t)n, sizeof(point) * (size_t)n, w->stream));
+            CU(mhdev_stream_sync(w->stream));
+            leave_device(w->device, prev);
+            prev = -1;
+            for (int i = 0; i < S; i++) {
+                mhContext *c = ctx->shards[i];
+                CU(enter_device(c->device, &prev));
+                CU(mhdev_h2d(ds[i].d_ref, ref, sizeof(point) * (size_t)n, c->stream));
+                CU(mhdev_stream_sync(c->stream));               /* `ref` is pageable and reused */
+                leave_device(c->device, prev);
+                prev = -1;
+            }
+        }
+    }
+    rc = found;
+    goto done;
+fail:
+    if (prev >= 0) mhdev_set_device(prev);
+done:
+    for (int i = 0; ds && i < S; i++) {
+        mhContext *c = ctx->shards[i];
+        int p2 = -1;
+        if (!enter_device(c->device, &p2)) {
+            mhdev_stream_sync(c->stream);
+            mhdev_free(ds[i].d_mind, c->stream); mhdev_free(ds[i].d_keys, c->stream); mhdev_free(ds[i].d_ref, c->stream);
+            leave_device(c->device, p2);
+        }
+    }
+    free(ds); free(ref);
+    return rc;
+}
+
 MH_API int KernelTopKDistinct(mhContext *ctx, int k, float minDistance, float rotWeight, int *chains, float *totals)
 {
     int prev = -1, rc = -1, found = 0;
@@ -1265,8 +1349,8 @@ MH_API int KernelTopKDistinct(mhContext *ctx, int k, float minDistance, float ro
     uint64_t *hk = NULL;
     g_err[0] = 0;
     if (!ctx || k < 1 || !(minDistance >= 0.f) || !(rotWeight >= 0.f)) { set_err("", "bad arguments", 0); return -1; }
-    if (IS_MULTI(ctx)) return multi_unsupported("KernelTopKDistinct (the layouts to compare live on different devices)");
     if (k > ctx->n_chains) k = ctx->n_chains;
+    if (IS_MULTI(ctx)) return topk_distinct_multi(ctx, k, minDistance, rotWeight, chains, totals);
     hk = (uint64_t *)malloc(8 * (size_t)k);
     if (!hk) { set_err("", "out of host memory", 0); return -1; }
     CU(enter_device(ctx->device, &prev));
@@ -1279,7 +1363,7 @@ MH_API int KernelTopKDistinct(mhContext *ctx, int k, float minDistance, float ro
     CU(mhdev_memset(d_keys, 0, 8 * (size_t)k, ctx->stream));
     for (int r = 0; r < k; r++) {
         CU(mhdev_launch_distinct_round(ctx->d_costs, ctx->d_points, ctx->n, ctx->n_chains, r, minDistance, rotWeight, (float)(2 * MH_PI),
-                                       d_mind, d_keys, ctx->stream));
+                                       d_mind, d_keys, NULL, ctx->stream));
         ctx->launches++;
     }
     CU(mhdev_d2h(hk, d_keys, 8 * (size_t)k, ctx->stream));

@@ -126,9 +126,10 @@ int mhdev_launch_topk(const void *d_costs, int n_chains, int k, void *d_work, vo
 /* Distinct suggestions, round r of k (all rounds are enqueued back to back, no host round trip): the chain
  * picked in round r-1 is read from d_keys[r-1] ON THE DEVICE; every chain's d_mind = min(d_mind, distance to
  * that pick's layout) (round 0: d_mind = +inf); then d_keys[r] = rank key of the best chain with
- * d_mind > min_dist.  d_keys[0..k) must be zeroed before round 0. */
+ * d_mind > min_dist.  d_keys[0..k) must be zeroed before round 0.  d_ref_layout != NULL: the previous pick's layout
+ * (n point records on THIS device, handed over by the host: multi-device contexts) instead of d_keys[r-1]. */
 int mhdev_launch_distinct_round(const void *d_costs, const void *d_points, int n, int n_chains, int round, float min_dist,
-                                float rot_weight, float two_pi, float *d_mind, void *d_keys, void *stream);
+                                float rot_weight, float two_pi, float *d_mind, void *d_keys, const void *d_ref_layout, void *stream);
 /* d_key (device int64) = order-preserving (totalCosts, GLOBAL chain id) key of the arg-max rank key. */
 int mhdev_launch_bestkey(const void *d_rank_key, uint64_t chain_offset, uint64_t chain_stride, void *d_key, void *stream);
 /* Largest dynamic shared memory per block and SM count / clock of the current device. */

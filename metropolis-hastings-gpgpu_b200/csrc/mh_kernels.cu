@@ -675,15 +675,18 @@ __global__ void __launch_bounds__(kTopkThreads) mh_topk_stage_kernel(const Costs
 // displacement of any object, max_i max(|dx|, |dy|, rot_weight |drot|) with the rotation difference wrapped into
 // [0, PI]; mind[chain] keeps the minimum over the picks so far.  One warp per chain, lanes over objects.  The
 // previous round's pick is read from keys[round - 1] on the device, so the host enqueues all rounds at once.
+// ref_ext != NULL (a context spread over several devices): the previous pick's layout was handed over by the host,
+// it may live on another device.
 __global__ void __launch_bounds__(256) mh_distinct_round_kernel(const Costs8 *__restrict__ costs, const PointRec *__restrict__ points, int n,
                                                                 int n_chains, int round, float min_dist, float rot_weight, float two_pi,
-                                                                float *__restrict__ mind, unsigned long long *keys)
+                                                                float *__restrict__ mind, unsigned long long *keys,
+                                                                const PointRec *__restrict__ ref_ext)
 {
-    int ref = -1;
-    if (round > 0) {
+    const PointRec *ref_layout = ref_ext;
+    if (round > 0 && !ref_ext) {
         const unsigned long long pk = keys[round - 1];
         if (pk == 0ull) return;                                 // nothing was left in the previous round (uniform over the grid)
-        ref = (int)(0xFFFFFFFFu - (uint32_t)pk);
+        ref_layout = points + (size_t)(0xFFFFFFFFu - (uint32_t)pk) * n;
     }
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -691,7 +694,7 @@ __global__ void __launch_bounds__(256) mh_distinct_round_kernel(const Costs8 *__
     for (int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chain < n_chains; chain += warps) {
         float m = INFINITY;
         if (round > 0) {
-            const PointRec *a = points + (size_t)chain * n, *b = points + (size_t)ref * n;
+            const PointRec *a = points + (size_t)chain * n, *b = ref_layout;
             float d = 0.f;
             for (int i = lane; i < n; i += 32) {
                 const PointRec p = a[i], q = b[i];
@@ -903,11 +906,11 @@ int mhdev_launch_topk(const void *d_costs, int n_chains, int k, void *d_work, vo
 }
 
 int mhdev_launch_distinct_round(const void *d_costs, const void *d_points, int n, int n_chains, int round, float min_dist,
-                                float rot_weight, float two_pi, float *d_mind, void *d_keys, void *stream)
+                                float rot_weight, float two_pi, float *d_mind, void *d_keys, const void *d_ref_layout, void *stream)
 {
     mh::mh_distinct_round_kernel<<<rank_grid((long long)n_chains * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const mh::Costs8 *>(d_costs), static_cast<const mh::PointRec *>(d_points), n, n_chains, round, min_dist, rot_weight,
-        two_pi, d_mind, static_cast<unsigned long long *>(d_keys));
+        two_pi, d_mind, static_cast<unsigned long long *>(d_keys), static_cast<const mh::PointRec *>(d_ref_layout));
     return (int)cudaGetLastError();
 }
 

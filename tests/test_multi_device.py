@@ -63,7 +63,10 @@ def test_multi_device_context_calls(kernel):
         many.run(30)
         one.run(30)
         assert one.results()[0].tobytes() == many.results()[0].tobytes()
-        for call in (many.device_results, lambda: many.set_stream(0), lambda: many.best_key(8), lambda: many.top_k_distinct(3, 0.5)):
+        for min_d, rw in ((0.75, 0.0), (1.0, 0.5), (1e9, 0.0)):  # distinct top-k: the picks' layouts cross devices through the host
+            a, b = one.top_k_distinct(9, min_d, rw), many.top_k_distinct(9, min_d, rw)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (min_d, rw)
+        for call in (many.device_results, lambda: many.set_stream(0), lambda: many.best_key(8)):
             with pytest.raises(pkg.KernelError, match="multi-device"):
                 call()
     # traces
