@@ -31,6 +31,7 @@
 
 #define MH_TLS __thread
 #define MH_MEMO_MIN_OBJS 28 /* nObjs from which MH_EVAL_FULL runs in its bit-identical memo form (measured: -7 % at 24, -2 % at 26, +10 % at 28, +19 % at 32, +27 % at 50, 2.2x at 100, 3.4x at 200) */
+#define MH_MAX_CHUNKS 8
 #define MH_MAX_BLOCKS_PER_SM 4 /* 128-thread blocks at the chain kernel's register cap (MH_MIN_BLOCKS in mh_kernels.cu) */
 
 static MH_TLS char g_err[512];
@@ -354,8 +355,13 @@ struct mhContext {
     float *d_x, *d_y, *d_rot, *d_cur, *d_best, *d_beta, *d_beta_snap;
     uint16_t *d_perm;
     void *d_points, *d_costs, *d_scratch, *d_exch_stats;
-    void *h_scratch;   /* 64 bytes of pinned host memory: small read-backs that must not block the host */
+    void *h_scratch;   /* a 64-byte pinned slot of the library's arena: small read-backs that must not block the host */
     float *ladder;     /* tempering: the current ladder, rung 0 first (host copy; chains hold a permutation of it) */
+    /* one-shot calls with a large result block: the chains run as n_chunks launches, and chunk j's scoring and D2H
+     * (on copy_stream) overlap the kernels of the chunks after it */
+    void *copy_stream;
+    void *chunk_ev[MH_MAX_CHUNKS];
+    int n_chunks, chunk_first[MH_MAX_CHUNKS + 1];
     void *stream;
     int own_stream;
     uint64_t it_done;  /* iterations already run (relative to opt.iteration_offset) */
@@ -500,7 +506,9 @@ static void ctx_free(mhContext *c)
     for (int i = 0; i < c->n_ev; i++) { mhdev_event_destroy(c->ev[i].e0); mhdev_event_destroy(c->ev[i].e1); }
     free(c->ev);
     free(c->ladder);
-    mhdev_host_free(c->h_scratch);
+    for (int j = 0; j < c->n_chunks; j++) mhdev_event_destroy(c->chunk_ev[j]);
+    if (c->copy_stream) mhdev_stream_destroy(c->copy_stream);
+    mhdev_scratch_release(c->h_scratch);
     if (c->own_stream) mhdev_stream_destroy(c->stream);
     free(c);
 }
@@ -696,7 +704,7 @@ static mhContext *create_single(const mhProblem *P, int nChains, const mhOptions
     CU(mhdev_malloc(&c->d_points, sizeof(point) * cn, c->stream));
     CU(mhdev_malloc(&c->d_costs, sizeof(resultCosts) * (size_t)nChains, c->stream));
     CU(mhdev_malloc(&c->d_scratch, 64, c->stream));
-    CU(mhdev_host_alloc(&c->h_scratch, 64));
+    CU(mhdev_scratch_acquire(&c->h_scratch));
     CU(mhdev_h2d(c->d_problem, P->blob, 4 * (size_t)c->problem_words, c->stream));
     if (c->opt.tempering_rungs > 1) CU(init_betas(c));
     CU(mhdev_stream_sync(c->stream)); /* the caller frees the blob */
@@ -713,7 +721,10 @@ static void destroy_single(mhContext *ctx)
     int prev = -1;
     const int dev = ctx->device;
     int e = enter_device(dev, &prev);
-    if (!e) mhdev_stream_sync(ctx->stream);
+    if (!e) {
+        if (ctx->copy_stream) mhdev_stream_sync(ctx->copy_stream);
+        mhdev_stream_sync(ctx->stream);
+    }
     ctx_free(ctx);
     if (prev >= 0) leave_device(dev, prev);
 }
@@ -852,13 +863,16 @@ static int drain_events(mhContext *c)
     return 0;
 }
 
-static int launch_segment(mhContext *c, int iterations, void *d_trace)
+/* One launch of the chain kernel over the chains [first, first + count) of the context (the whole context, or one
+ * chunk of a one-shot call).  A chain's result does not depend on which launch, block or lane runs it. */
+static int launch_chains_range(mhContext *c, int first, int count, int iterations, void *d_trace)
 {
     mhLaunch L;
+    const size_t fo = (size_t)first * (size_t)c->n;
     memset(&L, 0, sizeof L);
     L.d_problem = c->d_problem; L.problem_words = c->problem_words; L.smem_words = c->smem_words;
-    L.n = c->n; L.C = c->C; L.R = c->R; L.n_chains = c->n_chains; L.lanes = c->lanes; L.fresh = c->fresh;
-    L.seed = c->opt.seed; L.chain_offset = c->opt.chain_offset; L.chain_stride = c->opt.chain_stride;
+    L.n = c->n; L.C = c->C; L.R = c->R; L.n_chains = count; L.lanes = c->lanes; L.fresh = c->fresh;
+    L.seed = c->opt.seed; L.chain_offset = c->opt.chain_offset + (uint64_t)first * c->opt.chain_stride; L.chain_stride = c->opt.chain_stride;
     L.it_begin = c->opt.iteration_offset + c->it_done; L.it_count = iterations;
     L.schedule = c->opt.tempering_rungs > 1 ? MH_SCHED_PER_CHAIN : c->opt.schedule;
     L.schedule_length = c->opt.schedule_length;
@@ -867,8 +881,10 @@ static int launch_segment(mhContext *c, int iterations, void *d_trace)
     L.warps_per_block = c->delta_warps;
     L.beta_start = (float)c->opt.beta_start; L.beta_end = (float)c->opt.beta_end;
     L.beta_log2_ratio = log2f((float)(c->opt.beta_end / c->opt.beta_start));
-    L.d_x = c->d_x; L.d_y = c->d_y; L.d_rot = c->d_rot; L.d_perm = c->d_perm; L.d_cur_total = c->d_cur;
-    L.d_best_total = c->d_best; L.d_beta = c->d_beta; L.d_points = c->d_points; L.d_costs = c->d_costs; L.d_trace = d_trace;
+    L.d_x = c->d_x + fo; L.d_y = c->d_y + fo; L.d_rot = c->d_rot + fo; L.d_perm = c->d_perm + fo; L.d_cur_total = c->d_cur + first;
+    L.d_best_total = c->d_best + first; L.d_beta = c->d_beta + first;
+    L.d_points = (char *)c->d_points + sizeof(point) * fo; L.d_costs = (char *)c->d_costs + sizeof(resultCosts) * (size_t)first;
+    L.d_trace = d_trace;
     L.stream = c->stream;
     void *e0 = NULL, *e1 = NULL;
     int e = push_events(c, &e0, &e1);
@@ -884,6 +900,13 @@ static int launch_segment(mhContext *c, int iterations, void *d_trace)
         return e;
     }
     c->launches++;
+    return 0;
+}
+
+static int launch_segment(mhContext *c, int iterations, void *d_trace)
+{
+    int e = launch_chains_range(c, 0, c->n_chains, iterations, d_trace);
+    if (e) return e;
     c->fresh = 0;
     c->it_done += (uint64_t)iterations;
     c->costs_dirty = 1;
@@ -1051,14 +1074,11 @@ fail:
     return rc;
 }
 
-MH_API int KernelResults(mhContext *ctx, point *points, resultCosts *costs)
+/* Every device copies its slice straight into the caller's one block (no collective).
+ * A device-to-pageable-host copy blocks the calling thread, so each device gets a thread of its own and
+ * the copies share the host's memory bandwidth instead of queueing behind each other. */
+static int fetch_all_shards(mhContext *ctx, point *points, resultCosts *costs, void *(*worker)(void *))
 {
-    g_err[0] = 0;
-    if (!ctx) { set_err("", "null context", 0); return -1; }
-    if (!IS_MULTI(ctx)) return results_single(ctx, points, costs);
-    /* Every device copies its slice straight into the caller's one block (no collective).
-     * A device-to-pageable-host copy blocks the calling thread, so each device gets a thread of its own and
-     * the copies share the host's memory bandwidth instead of queueing behind each other. */
     const int S = ctx->n_shards;
     shardJob *jobs = (shardJob *)calloc((size_t)S, sizeof *jobs);
     pthread_t *th = (pthread_t *)calloc((size_t)S, sizeof *th);
@@ -1071,16 +1091,24 @@ MH_API int KernelResults(mhContext *ctx, point *points, resultCosts *costs)
         jobs[i].rc = -2;
     }
     for (int i = 1; i < S; i++)
-        if (pthread_create(&th[i], NULL, results_worker, &jobs[i])) jobs[i].rc = -3;   /* no thread: done inline below */
-    results_worker(&jobs[0]);
+        if (pthread_create(&th[i], NULL, worker, &jobs[i])) jobs[i].rc = -3;   /* no thread: done inline below */
+    worker(&jobs[0]);
     for (int i = 1; i < S; i++) {
-        if (jobs[i].rc == -3) results_worker(&jobs[i]);
+        if (jobs[i].rc == -3) worker(&jobs[i]);
         else pthread_join(th[i], NULL);
     }
     for (int i = 0; i < S; i++)
         if (jobs[i].rc) { memcpy(g_err, jobs[i].err, sizeof g_err); rc = -1; break; }
     free(jobs); free(th);
     return rc;
+}
+
+MH_API int KernelResults(mhContext *ctx, point *points, resultCosts *costs)
+{
+    g_err[0] = 0;
+    if (!ctx) { set_err("", "null context", 0); return -1; }
+    if (!IS_MULTI(ctx)) return results_single(ctx, points, costs);
+    return fetch_all_shards(ctx, points, costs, results_worker);
 }
 
 MH_API int KernelDeviceResults(mhContext *ctx, void **d_points, void **d_costs)
@@ -1641,6 +1669,111 @@ MH_API void KernelDestroy(mhContext *ctx)
     destroy_single(ctx);
 }
 
+/* ---- one-shot calls: chunked run, scoring and D2H of a chunk overlap the kernels of the chunks after it -------- */
+
+/* In how many launches a one-shot call runs this context's chains.  The D2H of the result block into the caller's
+ * pageable memory (~10-17 GB/s) is the one part of KernelWrapper that cannot be made faster -- but it can be hidden:
+ * with K chunks only the last chunk's copy is exposed.  One chunk per 48 MB of results, at most 8, never fewer than
+ * 8192 chains per chunk (every chunk must still fill the machine); env MH_CHUNKS overrides. */
+static int oneshot_chunks(const mhContext *c)
+{
+    const char *env = getenv("MH_CHUNKS");
+    if (c->opt.tempering_rungs > 1) return 1;                   /* ladders exchange between launches: one launch sequence */
+    int k;
+    if (env && *env) k = atoi(env);
+    else {
+        const double bytes = (double)c->n_chains * (double)c->n * (double)sizeof(point);
+        k = (int)(bytes / (48.0 * 1048576.0));
+        while (k > 1 && c->n_chains / k < 8192) k--;
+    }
+    if (k > MH_MAX_CHUNKS) k = MH_MAX_CHUNKS;
+    if (k > c->n_chains) k = c->n_chains;
+    return k < 1 ? 1 : k;
+}
+
+/* phase 0: every chunk's chain kernel on the context's stream, an event after each (asynchronous) */
+static int oneshot_enqueue(mhContext *c, int iterations)
+{
+    int prev = -1, rc = -1;
+    const int K = oneshot_chunks(c);
+    c->n_chunks = 0;
+    if (K <= 1) return run_iterations(c, iterations, NULL);
+    CU(enter_device(c->device, &prev));
+    if (c->opt.schedule_length <= 0 && c->opt.schedule != MH_SCHEDULE_CONSTANT) c->opt.schedule_length = iterations;
+    if (!c->copy_stream) CU(mhdev_stream_create(&c->copy_stream));
+    for (int j = 0; j <= K; j++) {
+        long long f = (long long)c->n_chains * j / K;
+        if (j > 0 && j < K) f = (f + 127) / 256 * 256;          /* whole blocks */
+        if (f > c->n_chains) f = c->n_chains;
+        c->chunk_first[j] = (int)f;
+    }
+    for (int j = 0; j < K; j++) {
+        const int first = c->chunk_first[j], count = c->chunk_first[j + 1] - first;
+        if (count > 0) CU(launch_chains_range(c, first, count, iterations, NULL));
+        CU(mhdev_event_create(&c->chunk_ev[j]));
+        c->n_chunks = j + 1;
+        CU(mhdev_event_record(c->chunk_ev[j], c->stream));
+    }
+    c->fresh = 0;
+    c->it_done += (uint64_t)iterations;
+    c->costs_dirty = 1;
+    rc = 0;
+fail:
+    if (prev >= 0) leave_device(c->device, prev);
+    return rc;
+}
+
+/* phase 1: chunk by chunk -- wait for its kernel, score it, copy it out (the copy blocks this thread, not the GPU) */
+static int oneshot_fetch(mhContext *c, point *points, resultCosts *costs)
+{
+    int prev = -1, rc = -1;
+    if (c->n_chunks == 0) return results_single(c, points, costs);
+    CU(enter_device(c->device, &prev));
+    for (int j = 0; j < c->n_chunks; j++) {
+        const int first = c->chunk_first[j], count = c->chunk_first[j + 1] - first;
+        const size_t fo = (size_t)first * (size_t)c->n;
+        CU(mhdev_stream_wait_event(c->copy_stream, c->chunk_ev[j]));
+        if (count <= 0) continue;
+        CU(mhdev_launch_score(c->d_problem, c->smem_words, c->n, c->C, c->R, count, c->score_lanes, (char *)c->d_points + sizeof(point) * fo,
+                              (char *)c->d_costs + sizeof(resultCosts) * (size_t)first, c->copy_stream));
+        c->launches++;
+        if (points) CU(mhdev_d2h(points + fo, (char *)c->d_points + sizeof(point) * fo, sizeof(point) * (size_t)count * (size_t)c->n, c->copy_stream));
+        if (costs) CU(mhdev_d2h(costs + first, (char *)c->d_costs + sizeof(resultCosts) * (size_t)first, sizeof(resultCosts) * (size_t)count, c->copy_stream));
+    }
+    CU(mhdev_stream_sync(c->copy_stream));
+    CU(mhdev_stream_sync(c->stream));
+    c->costs_dirty = 0;
+    rc = 0;
+fail:
+    for (int j = 0; j < c->n_chunks; j++) mhdev_event_destroy(c->chunk_ev[j]);
+    c->n_chunks = 0;
+    if (prev >= 0) leave_device(c->device, prev);
+    return rc;
+}
+
+static void *oneshot_worker(void *arg)
+{
+    shardJob *j = (shardJob *)arg;
+    j->rc = oneshot_fetch(j->c, j->points, j->costs);
+    if (j->rc) memcpy(j->err, g_err, sizeof j->err);
+    return NULL;
+}
+
+static int oneshot_run(mhContext *ctx, int iterations)
+{
+    if (!IS_MULTI(ctx)) return oneshot_enqueue(ctx, iterations);
+    for (int i = 0; i < ctx->n_shards; i++)
+        if (oneshot_enqueue(ctx->shards[i], iterations)) return -1;
+    return 0;
+}
+
+static int oneshot_results(mhContext *ctx, point *points, resultCosts *costs)
+{
+    g_err[0] = 0;
+    if (!IS_MULTI(ctx)) return oneshot_fetch(ctx, points, costs);
+    return fetch_all_shards(ctx, points, costs, oneshot_worker);
+}
+
 /* ---------------------------------------------------------------------------------------------
  * One-shot entry points
  * --------------------------------------------------------------------------------------------- */
@@ -1670,7 +1803,7 @@ MH_API result *KernelWrapperEx(const relationshipStruct *rss, const relationship
     resultCosts *costs = (resultCosts *)malloc(sizeof(resultCosts) * (size_t)chains);
     if (!pts || !res || !costs) { set_err("", "out of host memory", 0); goto fail; }
     clock_gettime(CLOCK_MONOTONIC, &ts[2]);
-    if (KernelRun(c, iterations)) goto fail;
+    if (oneshot_run(c, iterations)) goto fail;
     prefault(pts, sizeof(point) * (size_t)chains * (size_t)n); /* overlaps with the kernel, which is asynchronous */
     /* MH_PIN_RESULT=1: page-lock the (malloc'd, caller-owned) result block in place for the duration of the copy,
      * also while the kernel runs; the copy then runs at pinned-memory speed and, on a multi-device context, truly
@@ -1680,7 +1813,7 @@ MH_API result *KernelWrapperEx(const relationshipStruct *rss, const relationship
         pinned = mhdev_host_register(pts, sizeof(point) * (size_t)chains * (size_t)n) == 0;
     if (timing) KernelSynchronize(c);
     clock_gettime(CLOCK_MONOTONIC, &ts[3]);
-    const int res_rc = KernelResults(c, pts, costs);
+    const int res_rc = oneshot_results(c, pts, costs);
     if (pinned) mhdev_host_unregister(pts);
     if (res_rc) goto fail;
     clock_gettime(CLOCK_MONOTONIC, &ts[4]);

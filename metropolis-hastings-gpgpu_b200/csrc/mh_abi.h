@@ -155,7 +155,10 @@ int mhdev_stream_sync(void *stream);
 int mhdev_event_create(void **ev);
 void mhdev_event_destroy(void *ev);
 int mhdev_event_record(void *ev, void *stream);
+int mhdev_stream_wait_event(void *stream, void *ev);   /* work enqueued on `stream` after this call waits for `ev` */
 int mhdev_event_elapsed_ms(void *e0, void *e1, float *ms); /* synchronises on e1 */
+int mhdev_scratch_acquire(void **p);                        /* a 64-byte pinned read-back slot from the process-wide arena */
+void mhdev_scratch_release(void *p);
 int mhdev_host_alloc(void **p, size_t bytes);               /* pinned staging memory */
 void mhdev_host_free(void *p);
 int mhdev_host_register(void *p, size_t bytes);             /* page-lock caller memory in place (portable) */

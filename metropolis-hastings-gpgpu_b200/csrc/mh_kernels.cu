@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -1034,6 +1035,7 @@ int mhdev_event_create(void **ev)
     return (int)r;
 }
 void mhdev_event_destroy(void *ev) { if (ev) cudaEventDestroy(static_cast<cudaEvent_t>(ev)); }
+int mhdev_stream_wait_event(void *stream, void *ev) { return (int)cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(ev), 0); }
 int mhdev_event_record(void *ev, void *stream) { return (int)cudaEventRecord(static_cast<cudaEvent_t>(ev), static_cast<cudaStream_t>(stream)); }
 int mhdev_event_elapsed_ms(void *e0, void *e1, float *ms)
 {
@@ -1041,6 +1043,47 @@ int mhdev_event_elapsed_ms(void *e0, void *e1, float *ms)
     if (r != cudaSuccess) return (int)r;
     return (int)cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(e0), static_cast<cudaEvent_t>(e1));
 }
+// Small pinned read-back slots (64 bytes each) from ONE page-locked arena the library allocates once per process:
+// cudaMallocHost / cudaFreeHost per context were measured at 20-40 ms and up to 0.8 s on this driver (they
+// synchronise and re-map), which a one-shot call cannot afford.  A context takes a slot when it is created and gives
+// it back when it is destroyed; if the arena is exhausted the slot is plain (pageable) memory -- still correct, the
+// read-backs are followed by a stream synchronisation.
+static std::mutex g_scratch_mutex;
+static unsigned char *g_scratch_arena;
+static constexpr int kScratchSlots = 1024, kScratchBytes = 64;
+static unsigned char g_scratch_used[kScratchSlots];
+
+int mhdev_scratch_acquire(void **p)
+{
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    if (!g_scratch_arena) {
+        void *a = nullptr;
+        if (cudaMallocHost(&a, (size_t)kScratchSlots * kScratchBytes) == cudaSuccess) g_scratch_arena = static_cast<unsigned char *>(a);
+        else (void)cudaGetLastError();
+    }
+    if (g_scratch_arena)
+        for (int i = 0; i < kScratchSlots; i++)
+            if (!g_scratch_used[i]) {
+                g_scratch_used[i] = 1;
+                *p = g_scratch_arena + (size_t)i * kScratchBytes;
+                memset(*p, 0, kScratchBytes);
+                return 0;
+            }
+    *p = calloc(1, kScratchBytes);
+    return *p ? 0 : (int)cudaErrorMemoryAllocation;
+}
+
+void mhdev_scratch_release(void *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    unsigned char *q = static_cast<unsigned char *>(p);
+    if (g_scratch_arena && q >= g_scratch_arena && q < g_scratch_arena + (size_t)kScratchSlots * kScratchBytes)
+        g_scratch_used[(q - g_scratch_arena) / kScratchBytes] = 0;
+    else
+        free(p);
+}
+
 int mhdev_host_alloc(void **p, size_t bytes) { return (int)cudaMallocHost(p, bytes ? bytes : 16); }
 void mhdev_host_free(void *p) { if (p) cudaFreeHost(p); }
 int mhdev_host_register(void *p, size_t bytes) { return (int)cudaHostRegister(p, bytes, cudaHostRegisterPortable); }

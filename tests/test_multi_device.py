@@ -228,3 +228,24 @@ def test_ladder_tuning_retargets_the_chains(kernel):
     with kernel.create(room, 8, seed=1) as plain:
         with pytest.raises(pkg.KernelError, match="ladder"):
             plain.ladder(4)
+
+
+def test_chunked_one_shot_call_returns_the_same_bytes(kernel, monkeypatch):
+    """KernelWrapperEx runs a call with a large result block as several launches (chunks of chains) so that scoring
+    and the D2H of one chunk overlap the kernels of the next; a chain's result must not depend on the chunking.
+    MH_CHUNKS forces the chunk count (1 = one launch)."""
+    for cid, chains, iters, kw in ((2, 5000, 120, dict()), (3, 700, 60, dict(result_mode=1, beta_start=0.5, beta_end=6.0, schedule=1)),
+                                   (2, 3001, 80, dict(devices=[0, 0, 0])), (1, 5, 40, dict())):
+        room = S.make_config(cid)
+        monkeypatch.setenv("MH_CHUNKS", "1")
+        want = kernel.wrapper_ex(room, chains, iters, seed=9, **kw)
+        for chunks in ("2", "3", "8"):
+            monkeypatch.setenv("MH_CHUNKS", chunks)
+            got = kernel.wrapper_ex(room, chains, iters, seed=9, **kw)
+            assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes(), (cid, chunks)
+    monkeypatch.delenv("MH_CHUNKS")
+    room = S.make_config(4)                                      # the default rule: one chunk per 48 MB of results
+    a = kernel.wrapper_ex(room, 40000, 8, seed=2)                # 192 MB: 4 chunks
+    monkeypatch.setenv("MH_CHUNKS", "1")
+    b = kernel.wrapper_ex(room, 40000, 8, seed=2)
+    assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()

@@ -11,7 +11,7 @@ iters = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 k = pkg.Kernel(); room = pkg.synth.make_config(cid)
 k.wrapper_ex(room, 1024, 10, seed=1)
 print(f"config {cid}, {chains} chains x {iters} iterations, result block {chains * room.n * 24 / 1e6:.0f} MB, MH_PIN_RESULT={os.environ.get('MH_PIN_RESULT', '')}")
-for rep in range(3):
+for rep in range(4):
     t0 = time.perf_counter()
     res, pts, costs = k.wrapper_ex_raw(room, chains, iters, seed=3)
     t1 = time.perf_counter()
