@@ -228,7 +228,8 @@ MH_API int KernelTopKDistinct(mhContext *ctx, int k, float minDistance, float ro
  * the arrays of KernelTemperingState. */
 MH_API int KernelBestKey(mhContext *ctx, void *d_key);
 MH_API void KernelDecodeBestKey(long long key, unsigned long long *globalChain, float *total);
-/* Restart every chain from the caller's layout (iteration counter back to 0). */
+/* Restart every chain from the caller's layout (iteration counter back to 0).  A tempering context restarts on its
+ * CURRENT ladder (the tuned one, if KernelTemperingSetLadder was called). */
 MH_API int KernelReset(mhContext *ctx);
 /* Cross-GPU replica exchange (extension).  A context created with tempering_rungs > 1 and
  * chain_stride = S > 1 runs its chains at their current betas and never exchanges by itself.
