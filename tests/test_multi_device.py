@@ -249,3 +249,20 @@ def test_chunked_one_shot_call_returns_the_same_bytes(kernel, monkeypatch):
     monkeypatch.setenv("MH_CHUNKS", "1")
     b = kernel.wrapper_ex(room, 40000, 8, seed=2)
     assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
+
+
+def test_a_round_one_caller_with_the_short_options_struct_still_works(kernel):
+    """mhOptions grew from 88 to 136 bytes; struct_size says how much the caller filled in.  A caller compiled against
+    the round-1 header passes 88: whatever lies behind those 88 bytes must be ignored."""
+    import ctypes as C
+    room = S.make_config(1)
+    want = kernel.wrapper_ex(room, 50, 60, seed=4)
+    o = pkg.binding.make_options(seed=4)
+    o["n_devices"] = 9                                          # a tail that would be refused if it were read ("at most 8 devices")
+    o["struct_size"] = 88
+    g = np.zeros(1, L.gpuConfig)
+    g["gridxDim"], g["blockxDim"], g["iterations"] = 50, 64, 60
+    res = kernel.lib.KernelWrapperEx(*kernel._room_args(room), g.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p))
+    assert res, kernel.last_error()
+    got = kernel._unpack(res, 50, room.n)
+    assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes()
