@@ -139,7 +139,9 @@ def cpu_baseline(room, target_seconds=12.0):
     rate = chains * 400 / max(secs, 1e-6)
     iters = max(20, int(rate * target_seconds / chains))
     _, costs, secs, th = o.run(room, chains, iters, seed=1, timed=True, threads=threads)
-    return {"value": chains * iters / secs, "unit": UNIT, "cores": th, "kind": "port",
+    one_iters = max(20, int(rate / max(threads, 1) * 2.0))     # ~2 s of one core (single-core and all-core)
+    _, _, one_secs, _ = o.run(room, 1, one_iters, seed=1, timed=True, threads=1)
+    return {"value": chains * iters / secs, "unit": UNIT, "cores": th, "kind": "port", "single_core": one_iters / max(one_secs, 1e-9),
             "sample": f"{chains} chains x {iters} iterations of the same room ({secs:.1f} s), {flags} -ffp-contract=off, OpenMP",
             "seconds": secs, "best_totalCosts": float(costs["totalCosts"].max()),
             "median_final_totalCosts": float(np.median(costs["totalCosts"]))}
