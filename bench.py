@@ -216,7 +216,8 @@ def other_configs(k, pkg):
 def run_tempering(args, pkg, k, room, pl):
     """BASELINE config 5: the config-3 room under parallel tempering, TIME TO TARGET COST.  A ladder of 8 rungs
     (geometric beta 0.25 .. 8); with N > 1 GPUs the rungs of every ladder are spread over the ranks
-    (chain_stride = N) and neighbours exchange betas across NVLink: per epoch one all-gather of 8 bytes per chain.
+    (chain_stride = N) and neighbours exchange betas across NVLink: per epoch one all-gather of 8 bytes per chain
+    (--rungs / --exchange-interval change the ladder).
     Four samplers get the same budget (chains x iterations per GPU) on each of >= 3 seeds, the global best
     totalCosts (the sampler maximises it, quirk Q10) is read after every epoch:
       plain_beta2        the reference's sampler, BETA = 2 (Kernel.cu:33)
@@ -228,7 +229,8 @@ def run_tempering(args, pkg, k, room, pl):
     target = median over the seeds of plain_beta2's final global best; reported per sampler: in how many seeds and
     after how many seconds the target is first reached, and the best at the end of the budget."""
     torch, dist, rank, world, device = pl.torch, pl.dist, pl.rank, pl.world, pl.device
-    rungs, ex = 8, 100
+    rungs, ex = args.rungs, args.exchange_interval
+    assert rungs % world == 0 or world == 1, "the rungs of a ladder are spread evenly over the ranks"
     epochs = max(1, args.iterations // ex)
     iters = epochs * ex
     chains = max(rungs, args.chains - args.chains % rungs)
@@ -565,6 +567,8 @@ def main():
                          "3 plain scan (every term from scratch), 1 delta evaluation, 2 memo form")
     ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (other rooms, config 4 strong, config 2 as named, in-process multi-GPU)")
     ap.add_argument("--seeds", type=int, default=3, help="config 5: seeds per sampler")
+    ap.add_argument("--rungs", type=int, default=8, help="config 5: rungs per ladder (a multiple of --gpus)")
+    ap.add_argument("--exchange-interval", type=int, default=100, help="config 5: iterations between exchange epochs")
     ap.add_argument("--sub-steps", type=int, default=2, help="timed steps of the sub-records (config 4 strong, in-process multi-GPU)")
     args = ap.parse_args()
 
