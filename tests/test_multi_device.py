@@ -266,3 +266,33 @@ def test_a_round_one_caller_with_the_short_options_struct_still_works(kernel):
     assert res, kernel.last_error()
     got = kernel._unpack(res, 50, room.n)
     assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes()
+
+
+def test_interactive_session_from_plain_c(kernel, tmp_path):
+    """tests/c/interactive_session.c: the persistent context, stepping, distinct top-k and result fetch driven from
+    plain C through include/mh_kernel.h (one device and spread over three shards); its picks must be the Python
+    binding's for the same room, seed and options."""
+    root = os.path.dirname(HERE)
+    libdir = os.path.join(root, "metropolis-hastings-gpgpu_b200")
+    exe = tmp_path / "interactive_session"
+    subprocess.run(["gcc", "-std=c11", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(HERE, "c", "interactive_session.c"), "-o", str(exe), "-L", libdir, "-lKernel", "-Wl,-rpath," + libdir], check=True)
+    room = S.reference_main_fixture()
+    chains, steps = 300, 3
+    want = []
+    with kernel.create(room, chains, seed=2026, result_mode=1) as ctx:
+        for s in range(steps):
+            ctx.run(150)
+            idx, tot = ctx.top_k_distinct(4, 0.5, 0.25)
+            pts, _ = ctx.results()
+            for j, (i, t) in enumerate(zip(idx, tot)):
+                want.append(f"step {s} pick {j} chain {i} total {float(t).hex()} first {float(pts[i, 0]['x']).hex()} "
+                            f"{float(pts[i, 0]['y']).hex()} {float(pts[i, 0]['rotY']).hex()}")
+    for ndev in ("0", "3"):
+        out = subprocess.run([str(exe), str(chains), str(steps), ndev], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        got = []
+        for line in out.stdout.strip().splitlines():          # C prints %a, Python float.hex(): compare the values
+            f = line.split()
+            got.append(" ".join(f[:7] + [float.fromhex(f[7]).hex(), f[8]] + [float.fromhex(v).hex() for v in f[9:]]))
+        assert got == want, ndev
