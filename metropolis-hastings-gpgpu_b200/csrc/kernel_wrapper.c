@@ -248,6 +248,7 @@ static int pack_problem(const relationshipStruct *rss, const relationshipAngleSt
         b[H.off_pass + 2 * n + i] = (float)cfg[i].rotZ;
     }
     H.denom = denom;
+    H.inv_denom = (float)(1.0 / (double)denom);
     H.any_free = any_free;
     {   /* fixed-point clearance term: scale from the bounds of positions and rectangles, then the integer constants */
         double pos_bound = fmax(fmax(fabs((double)H.room_minx), fabs((double)H.room_maxx)), fmax(fabs((double)H.room_miny), fabs((double)H.room_maxy)));

@@ -30,7 +30,7 @@ typedef struct mhProblemHeader {
     float fdotu, two_focal_rot, cx2, cy2;  /* focal . u ; 2*focalRot ; centroid/2 (Q11)        */
     float room_minx, room_miny, room_maxx, room_maxy; /* AABB of surfaceRectangle             */
     float std_x, std_y, sigma_t, pi_cmp;   /* W/16, H/16 (Q19); 15/90*PI; largest float <= 3.1416 */
-    float two_pi, half_pi, two_pi_cmp, pad0; /* (float)6.2832, (float)1.5708, largest float <= 6.2832 */
+    float two_pi, half_pi, two_pi_cmp, inv_denom; /* (float)6.2832, (float)1.5708, largest float <= 6.2832, (float)(1 / denom) */
     int32_t off_obj_box;    /* float4[n] {min(v1x,v2x,v3x), min y, max x, max y} of the off-limit rect */
     int32_t off_obj_v0x;    /* float[n]  x of its first vertex, never translated (quirk Q6)   */
     int32_t off_obj_area;   /* float[n]  (float)(length*width)                                */

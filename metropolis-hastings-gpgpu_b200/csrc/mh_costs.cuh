@@ -50,6 +50,10 @@
 #define MH_CHECK(cond) ((void)0)
 #endif
 
+#ifndef MH_RECIP_DENOM
+#define MH_RECIP_DENOM 1
+#endif
+
 namespace mh {
 
 constexpr int kSymUnroll = MH_SYM_UNROLL; // columns per trip of the symmetry loop
@@ -276,9 +280,24 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 // cos(phi) of one object, phi = atan2(fy - y, fx - x) - rot + PI/2 (Kernel.cu:185-188, 271-277).
 // A pure function of that object's state, so it is memoised in the .w lane of its float4 and
 // recomputed only for the one or two objects a proposal moves.
+// MH_FOCAL_DIRECT (default): cos(theta - psi) with theta = atan2(dy, dx), psi = rot - PI/2 is
+// (dx cos psi + dy sin psi) / |d| -- one sincosf and one rsqrtf instead of atan2f and cosf: about half the
+// instructions and half the code on the per-iteration path (which is what this kernel is sensitive to); the value
+// differs from the reference's composition of two libm calls by rounding only (<= 3e-7 absolute).
+#ifndef MH_FOCAL_DIRECT
+#define MH_FOCAL_DIRECT 1
+#endif
 __device__ __noinline__ float focal_cos_impl(float fx, float fy, float half_pi, float x, float y, float rot)
 {
+#if MH_FOCAL_DIRECT
+    const float dx = fx - x, dy = fy - y;
+    const float d2 = fmaf(dx, dx, dy * dy);
+    float sn, cs;
+    sincosf(rot - half_pi, &sn, &cs);
+    return d2 > 0.f ? fmaf(dx, cs, dy * sn) * rsqrtf(d2) : cs;   // atan2(0, 0) = 0: cos(-psi)
+#else
     return cosf(atan2f(fy - y, fx - x) - rot + half_pi);
+#endif
 }
 __device__ __forceinline__ float focal_cos(const mhProblemHeader *h, float x, float y, float rot)
 {
@@ -575,7 +594,11 @@ __device__ __forceinline__ Costs8 combine(const mhProblemHeader *h, const RawTer
 {
     Costs8 c;
     c.pair = __fmul_rn(h->w_pair, __fmul_rn(t.pw, t.pa)); // (-pw)*(-pa): Q20
+#if MH_RECIP_DENOM
+    const float ax = t.vbx * h->inv_denom, ay = t.vby * h->inv_denom;   // (1 / sum of areas is a constant of the room)
+#else
     const float ax = t.vbx / h->denom, ay = t.vby / h->denom;
+#endif
     const float dX = ax - h->cx2, dY = ay - h->cy2;       // Q11
     c.visual = __fmul_rn(h->w_visual, -sqrtf(fmaf(dX, dX, dY * dY)));
     c.focal = __fmul_rn(h->w_focal, -t.focal);

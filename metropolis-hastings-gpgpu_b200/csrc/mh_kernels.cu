@@ -375,6 +375,8 @@ __global__ void __launch_bounds__(MH_DELTA_THREADS, MH_DELTA_MIN_BLOCKS) mh_delt
     TraceRec *trace = static_cast<TraceRec *>(L.d_trace);
     float beta = L.beta_start;
     if (L.schedule == MH_SCHED_PER_CHAIN) beta = L.d_beta[chain];
+    int recipe_mine = 0;                                        // this lane's share of the current batch of proposal recipes
+    float n0_mine = 0.f, n1_mine = 0.f, u_mine = 0.f;
 
     for (int k = 0; k < L.it_count; k++) {
         const uint64_t it = L.it_begin + (uint64_t)k;
@@ -388,35 +390,41 @@ __global__ void __launch_bounds__(MH_DELTA_THREADS, MH_DELTA_MIN_BLOCKS) mh_delt
         if (!EXACT && k > 0 && (it % (uint64_t)kRefresh) == 0)   // bound the drift of the running sums
             cur = delta_rebuild<G, kModeDelta>(P, S, D, c, g, sel, sums);
 
-        // -- random numbers: block 0 (the move) and block 1 (the acceptance uniform) of this iteration --
-        Philox4 w;
-        float u;
-        if (G >= 2) {
-            const Philox4 mine = draw_block<2>(L.seed, gchain, it, (uint32_t)(g & 1));
-            const int l0 = LM::first_lane(c), l1 = l0 + LM::xor_step;   // the group's lanes with g = 0 and g = 1
-            w.x = __shfl_sync(FULL, mine.x, l0);
-            w.y = __shfl_sync(FULL, mine.y, l0);
-            w.z = __shfl_sync(FULL, mine.z, l0);
-            w.w = __shfl_sync(FULL, mine.w, l0);
-            u = uniform01(__shfl_sync(FULL, mine.x, l1));
-        } else {
-            w = draw_block<2>(L.seed, gchain, it, 0);
-            u = uniform01(draw_block<2>(L.seed, gchain, it, 1).x);
+        // -- random numbers.  The stream is counter-based: what iteration k draws does not depend on what happened
+        //    before it.  So the G lanes of a group draw for G DIFFERENT iterations at once -- lane g computes the
+        //    whole proposal recipe of iteration k0 + g (Philox blocks 0 and 1, the re-draws while a picked object is
+        //    frozen, Box-Muller) -- and every iteration fetches its recipe from the lane that holds it with four
+        //    shuffles.  Same draws as computing them per iteration (same counters), but Philox, logf / sqrtf /
+        //    sincospif and the integer draws leave the per-iteration path on G - 1 of G iterations, and with them
+        //    the longest serial dependency chain before the evaluation can start. --
+        constexpr int B = G;                                    // iterations per batch (a power of two)
+        const int kb = k & (B - 1);
+        if (kb == 0) {                                          // (uniform over the warp)
+            const uint64_t itb = it + (uint64_t)g;
+            const Philox4 wb = draw_block<2>(L.seed, gchain, itb, 0);
+            u_mine = uniform01(draw_block<2>(L.seed, gchain, itb, 1).x);
+            const int pb = random_int(uniform01(wb.x), 2);
+            int ab = -1, bb = -1;
+            if (any_free && (pb != 2 || n >= 2)) {
+                uint32_t redraw = 2;
+                ab = random_int(uniform01(wb.y), n - 1);
+                if (pb == 2) bb = random_int(uniform01(wb.z), n - 1);
+                while (P.obj_frozen[ab] || (bb >= 0 && P.obj_frozen[bb])) {          // Kernel.cu:601, 637, 662, 666
+                    const Philox4 rw = draw_block<2>(L.seed, gchain, itb, redraw++);
+                    if (P.obj_frozen[ab]) ab = random_int(uniform01(rw.x), n - 1);
+                    if (bb >= 0 && P.obj_frozen[bb]) bb = random_int(uniform01(rw.y), n - 1);
+                }
+            }
+            box_muller(wb.z, wb.w, n0_mine, n1_mine);
+            recipe_mine = pb | ((ab + 1) << 2) | ((bb + 1) << 14);      // n <= 32 G <= 1024 in this kernel: 12 bits each
         }
+        const int src_lane = LM::first_lane(c) + kb * LM::xor_step;    // the lane of this group that drew for iteration k
+        const int recipe = __shfl_sync(FULL, recipe_mine, src_lane);
+        const float n0 = __shfl_sync(FULL, n0_mine, src_lane), n1 = __shfl_sync(FULL, n1_mine, src_lane);
+        const float u = __shfl_sync(FULL, u_mine, src_lane);
 
         // -- propose (Kernel.cu:576-704), the three moves side by side ----------------------------------
-        const int p = random_int(uniform01(w.x), 2);
-        int a = -1, b = -1;
-        if (any_free && (p != 2 || n >= 2)) {
-            uint32_t redraw = 2;
-            a = random_int(uniform01(w.y), n - 1);
-            if (p == 2) b = random_int(uniform01(w.z), n - 1);
-            while (P.obj_frozen[a] || (b >= 0 && P.obj_frozen[b])) {            // Kernel.cu:601, 637, 662, 666
-                const Philox4 rw = draw_block<2>(L.seed, gchain, it, redraw++);
-                if (P.obj_frozen[a]) a = random_int(uniform01(rw.x), n - 1);
-                if (b >= 0 && P.obj_frozen[b]) b = random_int(uniform01(rw.y), n - 1);
-            }
-        }
+        const int p = recipe & 3, a = ((recipe >> 2) & 0xFFF) - 1, b = ((recipe >> 14) & 0xFFF) - 1;
         const bool moved = a >= 0;
         MH_CHECK(a >= -1 && a < n && b >= -1 && b < n && (b < 0 || a >= 0));
         const int a_e = moved ? a : 0;                           // no move: "move" object 0 onto itself (all deltas are 0)
@@ -424,8 +432,6 @@ __global__ void __launch_bounds__(MH_DELTA_THREADS, MH_DELTA_MIN_BLOCKS) mh_delt
         const float4 ob = S.P4[WS::at(b >= 0 ? b : a_e, c)];
         float4 na = oa, nb = oa;
         {
-            float n0, n1;
-            box_muller(w.z, w.w, n0, n1);
             const float nx = oa.x + n0 * h->std_x, ny = oa.y + n1 * h->std_y;   // translate (Q19), snapped to the room
             const float tx = nx > room_x1 ? room_x1 : (nx < room_x0 ? room_x0 : nx);
             const float ty = ny > room_y1 ? room_y1 : (ny < room_y0 ? room_y0 : ny);

@@ -53,15 +53,25 @@ __device__ __forceinline__ Philox4 draw_block(uint64_t seed, uint64_t chain, uin
 // exact, so the value does not depend on FMA contraction.
 __device__ __forceinline__ float uniform01(uint32_t x) { return __fmaf_rn((float)x, 0x1p-32f, 0x1p-33f); }
 
-// curand_normal.h:70-92: first normal = s sin v, second = s cos v.
+// curand_normal.h:70-92: first normal = s sin v, second = s cos v, v = 2 pi (y + 0.5) / 2^32.
+// MH_BOX_MULLER_PI (default): sin and cos of v through sincospif((y + 0.5) / 2^31) -- the argument is exact and needs
+// no reduction by pi, which halves the code of this per-iteration helper (the memo kernel is sensitive to the length of
+// its per-iteration path); the normals differ from cuRAND's float-rounded v by <= 4e-7 s.
+#ifndef MH_BOX_MULLER_PI
+#define MH_BOX_MULLER_PI 1
+#endif
 __device__ __noinline__ float2 box_muller_pair(uint32_t x, uint32_t y)
 {
-    const float k = 1.46291807e-09f; // 2 pi / 2^32
     const float u = uniform01(x);
-    const float v = __fmaf_rn((float)y, k, k / 2.0f);
     const float s = sqrtf(-2.0f * logf(u));
     float sn, cs;
+#if MH_BOX_MULLER_PI
+    sincospif(__fmaf_rn((float)y, 0x1p-31f, 0x1p-32f), &sn, &cs);
+#else
+    const float k = 1.46291807e-09f; // 2 pi / 2^32
+    const float v = __fmaf_rn((float)y, k, k / 2.0f);
     sincosf(v, &sn, &cs);
+#endif
     return make_float2(s * sn, s * cs);
 }
 __device__ __forceinline__ void box_muller(uint32_t x, uint32_t y, float &n0, float &n1)
