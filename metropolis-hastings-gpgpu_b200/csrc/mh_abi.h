@@ -97,6 +97,10 @@ typedef struct mhLaunch {
     void *d_costs;          /* resultCosts[chain]                                              */
     void *d_trace;          /* mhTraceEntry[it][chain] or NULL                                 */
     void *stream;
+    /* A copy of the problem header.  The launch descriptor is the kernel's parameter, i.e. it lives in the constant
+     * bank: every scalar of the header the loops use (reflection axis, scales, weights, room bounds) becomes a
+     * constant operand of the arithmetic instruction that needs it instead of a shared-memory load + a register. */
+    mhProblemHeader hdr;
 } mhLaunch;
 
 int mhdev_launch_chains(const mhLaunch *l);

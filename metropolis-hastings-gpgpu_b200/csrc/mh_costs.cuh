@@ -84,10 +84,12 @@ struct SmemProblem {
     const int *clr_v0xq;
 };
 
-__device__ __forceinline__ SmemProblem bind_problem(const float *base)
+// base: the staged blob in shared memory (arrays); hdr: where the header's scalars are read from -- the blob itself,
+// or the copy in the kernel's parameter space (constant bank) that the chain kernels carry.
+__device__ __forceinline__ SmemProblem bind_problem(const float *base, const mhProblemHeader *hdr = nullptr)
 {
     SmemProblem P;
-    P.h = reinterpret_cast<const mhProblemHeader *>(base);
+    P.h = hdr ? hdr : reinterpret_cast<const mhProblemHeader *>(base);
     P.obj_box = reinterpret_cast<const float4 *>(base + P.h->off_obj_box);
     P.obj_v0x = base + P.h->off_obj_v0x;
     P.obj_area = base + P.h->off_obj_area;

@@ -93,14 +93,14 @@ __device__ __forceinline__ void write_points_warp(const WS &S, int cc, int n, co
 // less work for the same or a statistically equivalent result, MH_EVAL_MEMO and MH_EVAL_DELTA, are
 // mh_delta_kernel below.)
 template <int G>
-__global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const mhLaunch L)
+__global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const __grid_constant__ mhLaunch L)
 {
     using WS = WarpState<G, true>;
     constexpr int CPW = WS::CPW;
     extern __shared__ __align__(16) float smem[];
     const float *gprob = static_cast<const float *>(L.d_problem);
     stage_problem(smem, gprob, L.smem_words);
-    const SmemProblem P = bind_problem(smem);
+    const SmemProblem P = bind_problem(smem, &L.hdr);
     const mhProblemHeader *h = P.h;
     const int n = h->n, C = h->C;
 
@@ -308,14 +308,13 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
 // MODE = kModeExact: MH_EVAL_MEMO (exact_eval: every total bit-identical to the full evaluation's).
 // Neither keeps the plain scan's per-warp array of clearance rectangles: the clearance term is an integer sum
 // updated pair by pair (mh_costs.cuh), the old rectangles are rebuilt from the moved objects' old positions.
-#ifndef MH_DELTA_THREADS
-#define MH_DELTA_THREADS 256   // largest block of the memo kernels (8 warps) ...
-#endif
-#ifndef MH_DELTA_MIN_BLOCKS
-#define MH_DELTA_MIN_BLOCKS 2  // ... and the resident blocks per SM they are compiled for: 128 registers per thread
-#endif
-template <int G, int MODE>
-__global__ void __launch_bounds__(MH_DELTA_THREADS, MH_DELTA_MIN_BLOCKS) mh_delta_kernel(const mhLaunch L)
+// Two builds of every memo kernel: WPB = 8 for blocks of up to 8 warps, two per SM (128 registers per thread), and
+// WPB = 4 for blocks of 4 warps, five per SM (96 registers: no spill since the header's scalars come from the constant
+// bank).  Which one runs is the host's choice (choose_delta_shape: whichever keeps more warps resident given the
+// shared memory a chain needs): at 50 objects 5 x 4 warps beat 2 x 8 by 5 %, at 200 objects they lose 19 %.
+#define MH_DELTA_THREADS 256
+template <int G, int MODE, int WPB>
+__global__ void __launch_bounds__(WPB * 32, WPB == 4 ? 5 : 2) mh_delta_kernel(const __grid_constant__ mhLaunch L)
 {
     using WS = WarpState<G>;
     using DS = DeltaState<G>;
@@ -326,7 +325,7 @@ __global__ void __launch_bounds__(MH_DELTA_THREADS, MH_DELTA_MIN_BLOCKS) mh_delt
     extern __shared__ __align__(16) float smem[];
     const float *gprob = static_cast<const float *>(L.d_problem);
     stage_problem(smem, gprob, L.smem_words);
-    const SmemProblem P = bind_problem(smem);
+    const SmemProblem P = bind_problem(smem, &L.hdr);
     const mhProblemHeader *h = P.h;
     const int n = h->n, C = h->C;
     const int warps = blockDim.x >> 5;
@@ -750,17 +749,22 @@ template <int G> static int launch_scan_g(const mhLaunch &L)
     return (int)cudaGetLastError();
 }
 
-template <int G, int MODE> static int launch_delta_g(const mhLaunch &L)
+template <int G, int MODE, int WPB> static int launch_delta_w(const mhLaunch &L, int warps)
 {
     using WS = WarpState<G>;
-    const int warps = L.warps_per_block >= 1 && L.warps_per_block <= MH_DELTA_THREADS / 32 ? L.warps_per_block : 4;
     const int chains_per_block = warps * WS::CPW;
     const int blocks = (L.n_chains + chains_per_block - 1) / chains_per_block;
     const size_t smem = sizeof(float) * ((size_t)L.smem_words + (size_t)warps * (WS::words(L.n, 0) + DeltaState<G>::words(L.n, L.C, L.R, MODE)));
-    cudaError_t e = cudaFuncSetAttribute(mh_delta_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mh_delta_kernel<G, MODE, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    mh_delta_kernel<G, MODE><<<blocks, warps * 32, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
+    mh_delta_kernel<G, MODE, WPB><<<blocks, warps * 32, smem, static_cast<cudaStream_t>(L.stream)>>>(L);
     return (int)cudaGetLastError();
+}
+
+template <int G, int MODE> static int launch_delta_g(const mhLaunch &L)
+{
+    const int warps = L.warps_per_block >= 1 && L.warps_per_block <= MH_DELTA_THREADS / 32 ? L.warps_per_block : 4;
+    return warps <= 4 ? launch_delta_w<G, MODE, 4>(L, warps) : launch_delta_w<G, MODE, 8>(L, warps);
 }
 
 template <int G> static int launch_chains_g(const mhLaunch &L)
