@@ -12,7 +12,7 @@ headline metric, on the 50-object living room (config 3: n=50, C=25, R=50, 65536
                                                             (the reference has no multi-GPU path, Kernel.cu:951)
 
 One step = one pass of the hot path over the whole batch: every chain runs `iterations` MH steps
-from the caller's layout.  The library's default evaluation (MH_EVAL_FULL) runs, from 28 objects up, in
+from the caller's layout.  The library's default evaluation (MH_EVAL_FULL) runs, from 28 objects up (18 for big jobs), in
 its memo form: every proposal's costs, every accept decision and every returned bit equal the plain
 full re-evaluation's (tested), at a fraction of the work; the plain scan's rate is reported beside it.  `value` is timed with the problem and chain state already resident in
 HBM (KernelCreate once, then KernelReset + KernelRun per step, CUDA events around the kernel);
@@ -208,7 +208,7 @@ def other_configs(k, pkg):
         out[f"config{cid}"] = e
     room = pkg.synth.make_config(3)
     out["config3_delta_eval"] = quick_rate(k, room, 65536, 512, eval_mode=1)
-    out["note"] = ("full_eval = the library default (bit-identical memo form from 28 objects up); full_eval_plain_scan = every term "
+    out["note"] = ("full_eval = the library default (bit-identical memo form from 18-28 objects up); full_eval_plain_scan = every term "
                    "from scratch; delta_eval = incremental running sums, statistically equivalent (MH_EVAL_DELTA)")
     return out
 

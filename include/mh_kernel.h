@@ -46,7 +46,8 @@ enum {
 
 enum {
     MH_EVAL_FULL = 0, /* every proposal re-evaluates every live cost term from scratch (Kernel.cu:804); for
-                         nObjs >= 28 the library uses the bit-identical MH_EVAL_MEMO form, which is faster  */
+                         nObjs >= 28 (>= 18 for jobs of 8192 chains and more) the library uses the bit-identical
+                         MH_EVAL_MEMO form, which is faster                                               */
     MH_EVAL_FULL_SCAN = 3, /* MH_EVAL_FULL with the plain n^2 scan forced (verification)                    */
     MH_EVAL_MEMO = 2, /* full evaluation through exact memos (symmetry row minima, relationship penalties,
                          surface values, clearance row sums): totals bit-identical to MH_EVAL_FULL_SCAN

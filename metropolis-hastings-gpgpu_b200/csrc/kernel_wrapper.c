@@ -30,7 +30,13 @@
 #endif
 
 #define MH_TLS __thread
-#define MH_MEMO_MIN_OBJS 28 /* nObjs from which MH_EVAL_FULL runs in its bit-identical memo form (measured: -7 % at 24, -2 % at 26, +10 % at 28, +19 % at 32, +27 % at 50, 2.2x at 100, 3.4x at 200) */
+/* nObjs from which MH_EVAL_FULL runs in its bit-identical memo form.  Measured on B200 with 65536 chains, memo
+ * against plain scan (profiles/r2_probe_logs/ab_scan_memo_crossover.log): 16 objects -17 %, 18 +23 %, 20 +1 %,
+ * 22 +12 %, 24 +25 %, 26 +30 %, 28 +68 %, 50 2.3x, 200 8.7x.  With few chains the scan holds out longer (1024 chains
+ * of 16 objects: scan 4.2e8 against 2.9e8), so the lower threshold applies to jobs of at least 8192 chains. */
+#define MH_MEMO_MIN_OBJS 28
+#define MH_MEMO_MIN_OBJS_BIG_JOB 18
+#define MH_BIG_JOB_CHAINS 8192
 #define MH_MAX_CHUNKS 8
 #define MH_MAX_BLOCKS_PER_SM 4 /* 128-thread blocks at the chain kernel's register cap (MH_MIN_BLOCKS in mh_kernels.cu) */
 
@@ -672,7 +678,8 @@ static mhContext *create_single(const mhProblem *P, int nChains, const mhOptions
     uint64_t job = c->opt.total_chains ? c->opt.total_chains : (uint64_t)nChains;
     if (job < (uint64_t)nChains) job = (uint64_t)nChains;
     const int job_chains = job > 0x7fffffffull ? 0x7fffffff : (int)job;
-    if (c->opt.eval_mode == MH_EVAL_FULL && c->n >= MH_MEMO_MIN_OBJS && !getenv("MH_FULL_SCAN")) {
+    const int memo_min = job_chains >= MH_BIG_JOB_CHAINS ? MH_MEMO_MIN_OBJS_BIG_JOB : MH_MEMO_MIN_OBJS;
+    if (c->opt.eval_mode == MH_EVAL_FULL && c->n >= memo_min && !getenv("MH_FULL_SCAN")) {
         if (choose_delta_shape(c->n, c->C, c->R, c->smem_words, job_chains, nChains, c->opt.lanes_per_chain, MH_EVAL_MEMO, &c->lanes, &c->delta_warps) == 0)
             c->eval_internal = MH_EVAL_MEMO;
         else
