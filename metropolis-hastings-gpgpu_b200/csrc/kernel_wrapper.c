@@ -440,7 +440,9 @@ static int choose_lanes(int n, int C, int R, int smem_words, int n_chains, int r
         /* warp instructions of the whole job: with chains to spare this is proportional to G (the old form of
          * the model); with fewer chains than a warp holds it is not -- one chain is one warp for every G, and
          * the widest group, i.e. the shortest per-lane program, wins (measured: 13.7 -> 3.0 ms for 1 chain x 1000 iterations at n=16) */
-        const double cost = warps_total * (450.0 + rows * (12.0 * n + 8.0 * C + 100.0));
+        /* (the work every lane repeats: ~150 instructions per iteration, plus ~300 of drawing the proposal recipe, which
+         * the lanes of a group share -- one iteration per lane, mh_kernels.cu) */
+        const double cost = warps_total * (150.0 + 300.0 / G + rows * (12.0 * n + 8.0 * C + 100.0));
         const double score = cover / cost;
         if (score > best_score * 1.03) { /* near-ties go to the wider group (less shared memory) */
             best_score = score;

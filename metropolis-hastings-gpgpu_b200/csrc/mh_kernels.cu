@@ -156,6 +156,9 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
     float beta = L.beta_start;
     if (L.schedule == MH_SCHED_PER_CHAIN) beta = L.d_beta[chain];
 
+    int pa_mine = 0, b_mine = -1;                               // this lane's share of the current batch of proposal recipes
+    float n0_mine = 0.f, n1_mine = 0.f, u_mine = 0.f;
+
     // ---- the chain (Kernel.cu:785-827, Semantics S of SURVEY.md section 8a) ---------------------
     for (int k = 0; k < L.it_count; k++) {
         const uint64_t it = L.it_begin + (uint64_t)k;
@@ -167,48 +170,56 @@ __global__ void __launch_bounds__(THREADS, MH_MIN_BLOCKS) mh_chain_kernel(const 
                                                     : L.beta_start + (L.beta_end - L.beta_start) * tt;
         }
 
-        // -- propose (Kernel.cu:576-704): every lane of the group derives the same move; the two Philox
-        //    blocks of the iteration (move, acceptance uniform) are computed by different lanes at once --
-        Philox4 w;
-        float u;
-        if (G >= 8) {                                          // (narrower groups: measured neutral to -2 %)
-            const Philox4 mine = draw_block(L.seed, gchain, it, (uint32_t)(g & 1));
-            const int l0 = LM::first_lane(c);
-            w.x = __shfl_sync(0xffffffffu, mine.x, l0);
-            w.y = __shfl_sync(0xffffffffu, mine.y, l0);
-            w.z = __shfl_sync(0xffffffffu, mine.z, l0);
-            w.w = __shfl_sync(0xffffffffu, mine.w, l0);
-            u = uniform01(__shfl_sync(0xffffffffu, mine.x, l0 + 1));
-        } else {
-            w = draw_block(L.seed, gchain, it, 0);
-            u = uniform01(draw_block(L.seed, gchain, it, 1).x);
+        // -- propose (Kernel.cu:576-704).  The stream is counter-based, so the G lanes of a group draw the proposal
+        //    recipes of G DIFFERENT iterations at once (lane g: iteration k0 + g -- Philox blocks 0 and 1, the re-draws
+        //    while a picked object is frozen, Box-Muller) and every iteration fetches its recipe with five shuffles:
+        //    the same draws, off the per-iteration path on G - 1 of G iterations (see mh_delta_kernel).  One lane per
+        //    chain: nothing to share, every iteration draws for itself. --
+        int p, a = -1, b = -1;
+        float n0, n1, u;
+        if (G == 1 || (k & (G - 1)) == 0) {                    // (uniform over the warp)
+            const uint64_t itb = it + (uint64_t)g;
+            const Philox4 wb = draw_block(L.seed, gchain, itb, 0);
+            u_mine = uniform01(draw_block(L.seed, gchain, itb, 1).x);
+            const int pb = random_int(uniform01(wb.x), 2);
+            int ab = -1, bb = -1;
+            if (any_free && (pb != 2 || n >= 2)) {
+                uint32_t redraw = 2;
+                ab = random_int(uniform01(wb.y), n - 1);
+                if (pb == 2) bb = random_int(uniform01(wb.z), n - 1);
+                while (P.obj_frozen[ab] || (bb >= 0 && P.obj_frozen[bb])) {       // Kernel.cu:601, 637, 662, 666
+                    const Philox4 rw = draw_block(L.seed, gchain, itb, redraw++);
+                    if (P.obj_frozen[ab]) ab = random_int(uniform01(rw.x), n - 1);
+                    if (bb >= 0 && P.obj_frozen[bb]) bb = random_int(uniform01(rw.y), n - 1);
+                }
+            }
+            box_muller(wb.z, wb.w, n0_mine, n1_mine);
+            pa_mine = pb | ((ab + 1) << 2);
+            b_mine = bb;
         }
-        const int p = random_int(uniform01(w.x), 2);
-        int a = -1, b = -1;
+        if (G == 1) {
+            p = pa_mine & 3; a = (pa_mine >> 2) - 1; b = b_mine; n0 = n0_mine; n1 = n1_mine; u = u_mine;
+        } else {
+            const int src_lane = LM::first_lane(c) + (k & (G - 1));     // the lane of this group that drew for iteration k
+            const int pa = __shfl_sync(0xffffffffu, pa_mine, src_lane);
+            p = pa & 3; a = (pa >> 2) - 1;
+            b = __shfl_sync(0xffffffffu, b_mine, src_lane);
+            n0 = __shfl_sync(0xffffffffu, n0_mine, src_lane);
+            n1 = __shfl_sync(0xffffffffu, n1_mine, src_lane);
+            u = __shfl_sync(0xffffffffu, u_mine, src_lane);
+        }
         float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;   // proposed state of objects a, b
         float4 oa = na, ob = na;                                // state to restore on rejection
-        if (any_free && (p != 2 || n >= 2)) {
-            uint32_t redraw = 2;
-            a = random_int(uniform01(w.y), n - 1);
-            if (p == 2) b = random_int(uniform01(w.z), n - 1);
-            while (P.obj_frozen[a] || (b >= 0 && P.obj_frozen[b])) {            // Kernel.cu:601, 637, 662, 666
-                const Philox4 rw = draw_block(L.seed, gchain, it, redraw++);
-                if (P.obj_frozen[a]) a = random_int(uniform01(rw.x), n - 1);
-                if (b >= 0 && P.obj_frozen[b]) b = random_int(uniform01(rw.y), n - 1);
-            }
+        if (a >= 0) {
             MH_CHECK(a >= 0 && a < n && b >= -1 && b < n);
             oa = S.P4[WS::at(a, c)];
             na = oa;
             if (p == 0) {                                      // translate, sigma = W/16, H/16 (Q19), snap to the room
-                float n0, n1;
-                box_muller(w.z, w.w, n0, n1);
                 const float nx = oa.x + n0 * h->std_x, ny = oa.y + n1 * h->std_y;
                 na.x = nx > room_x1 ? room_x1 : (nx < room_x0 ? room_x0 : nx);
                 na.y = ny > room_y1 ? room_y1 : (ny < room_y0 ? room_y0 : ny);
                 na.w = focal_cos(h, na.x, na.y, na.z);
             } else if (p == 1) {                               // rotate, one wrap into [0, 2 PI] (Kernel.cu:645-651)
-                float n0, n1;
-                box_muller(w.z, w.w, n0, n1);
                 float ar = oa.z + n0 * h->sigma_t;
                 if (ar < 0.f) ar += h->two_pi;
                 else if (ar > h->two_pi_cmp) ar -= h->two_pi;
