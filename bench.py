@@ -44,7 +44,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 METRIC = "MH proposals evaluated/sec (chains x iters/s) at 50 objects"
-PROFILE_FILE = "r2a_memo_n50_g8_ncu_full.txt"   # ncu --set full capture of the default kernel at 65536 chains
+PROFILE_FILE = "r2g_memo_n50_g8_ncu_full.txt"   # ncu --set full capture of the default kernel at 65536 chains
 UNIT = "proposals/s"
 
 
