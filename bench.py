@@ -213,15 +213,38 @@ def other_configs(k, pkg):
     return out
 
 
+def config3_annealing(k, room, chains, iterations):
+    """"run once with fixed beta = 2 and once with the annealing extension".  Same room, chain
+    count, iteration budget and seed; the sampler maximises totalCosts (quirk Q10), so higher is better.  The schedule is
+    evaluated inside the chain kernel (one beta per iteration), so the rate is the fixed-beta kernel's."""
+    import numpy as np
+    out = {"chains": chains, "iterations": iterations,
+           "note": "kernel-only rate (CUDA events) and the totalCosts the chains end on: the global best, the median and the 99th "
+                   "percentile of the per-chain finals; result_mode = final layout in both runs"}
+    for name, opts in (("fixed_beta2", {}),
+                       ("geometric_0.5_to_8", dict(beta_start=0.5, beta_end=8.0, schedule=1, schedule_length=iterations)),
+                       ("linear_0.5_to_8", dict(beta_start=0.5, beta_end=8.0, schedule=2, schedule_length=iterations))):
+        with k.create(room, chains, seed=7, **opts) as ctx:
+            ctx.run(iterations)
+            ctx.synchronize()
+            ms, _ = ctx.stats()
+            _, costs = ctx.results()
+        t = costs["totalCosts"].astype(np.float64)
+        out[name] = {"proposals_per_s": chains * iterations / (ms * 1e-3), "best_totalCosts": float(t.max()),
+                     "median_final_totalCosts": float(np.median(t)), "p99_final_totalCosts": float(np.percentile(t, 99))}
+    return out
+
+
 def run_tempering(args, pkg, k, room, pl):
     """BASELINE config 5: the config-3 room under parallel tempering, TIME TO TARGET COST.  A ladder of 8 rungs
     (geometric beta 0.25 .. 8); with N > 1 GPUs the rungs of every ladder are spread over the ranks
     (chain_stride = N) and neighbours exchange betas across NVLink: per epoch one all-gather of 8 bytes per chain
     (--rungs / --exchange-interval change the ladder).
-    Four samplers get the same budget (chains x iterations per GPU) on each of >= 3 seeds, the global best
+    Five samplers get the same budget (chains x iterations per GPU) on each of >= 3 seeds, the global best
     totalCosts (the sampler maximises it, quirk Q10) is read after every epoch:
       plain_beta2        the reference's sampler, BETA = 2 (Kernel.cu:33)
       plain_beta8        plain MH at the ladder's coldest beta
+      anneal_geometric   plain chains, beta annealed geometrically from the ladder's hottest to its coldest beta over the budget
       tempering_fixed    the geometric ladder, exchange every 100 iterations
       tempering_adapted  the same, the ladder re-tuned every 5 epochs during the first 30 % of the run from the
                          exchange statistics (KernelTemperingStats -> KernelTemperingProposeLadder ->
@@ -243,6 +266,9 @@ def run_tempering(args, pkg, k, room, pl):
         if kind.startswith("plain"):
             beta = 2.0 if kind == "plain_beta2" else 8.0
             return k.create(room, chains, seed=seed, chain_offset=rank * chains, total_chains=total, beta_start=beta)
+        if kind == "anneal_geometric":
+            return k.create(room, chains, seed=seed, chain_offset=rank * chains, total_chains=total, beta_start=0.25, beta_end=8.0,
+                            schedule=1, schedule_length=iters)
         opts = dict(seed=seed, beta_start=0.25, beta_end=8.0, tempering_rungs=rungs, exchange_interval=ex, total_chains=total)
         if world > 1:
             return k.create(room, chains, chain_offset=rank, chain_stride=world, **opts)
@@ -285,7 +311,7 @@ def run_tempering(args, pkg, k, room, pl):
         ctx.close()
         return out
 
-    kinds = ("plain_beta2", "plain_beta8", "tempering_fixed", "tempering_adapted")
+    kinds = ("plain_beta2", "plain_beta8", "anneal_geometric", "tempering_fixed", "tempering_adapted")
     one_run("tempering_fixed", 1)                               # warm-up: every kernel compiled and loaded, pools filled
     sampler = ClockSampler(pl.local_rank) if rank == 0 else None
     runs = {kind: [one_run(kind, s) for s in seeds] for kind in kinds}
@@ -694,6 +720,7 @@ def main():
         if not args.no_extras and world == 1:                    # the side measurements run at N=1 only
             line["config2_as_named"] = config2_as_named(k, pkg, with_reference=not args.no_ref_gpu)
             line["other_configs_kernel_only"] = other_configs(k, pkg)
+            line["config3_annealing"] = config3_annealing(k, room, args.chains, min(args.iterations, 10000))
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_baseline(room)
             line["cpu_baseline"] = cb
