@@ -650,7 +650,7 @@ def main():
                     "gpu_launches": m["launches"], "clocks": m["clocks"], "device": info["name"],
                     "roofline": {"bound": "fp32", "achieved": per_gpu * f_live / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
                                  "frac": per_gpu * f_live / 1e12 / peak_tflops, "effective": True, "traffic": None,
-                                 "kernel": "mh_delta_kernel<32, exact + clearance row sums>", "kernel_ms_per_launch": m["kernel_ms_per_launch"]},
+                                 "kernel": "mh_delta_kernel<32, exact, 8>", "kernel_ms_per_launch": m["kernel_ms_per_launch"]},
                     "config4_strong": c4}
             print(json.dumps(line), flush=True)
         if world > 1:

@@ -50,7 +50,8 @@ enum {
                          MH_EVAL_MEMO form, which is faster                                               */
     MH_EVAL_FULL_SCAN = 3, /* MH_EVAL_FULL with the plain n^2 scan forced (verification)                    */
     MH_EVAL_MEMO = 2, /* full evaluation through exact memos (symmetry row minima, relationship penalties,
-                         surface values, clearance row sums): totals bit-identical to MH_EVAL_FULL_SCAN
+                         surface values; the clearance term is an exact integer sum updated pair by
+                         pair): totals bit-identical to MH_EVAL_FULL_SCAN
                          for the same lane width                                                         */
     MH_EVAL_DELTA = 1 /* incremental evaluation: only what the moved objects touch is recomputed, running
                          sums rebuilt from scratch every 128 iterations; statistically equivalent to

@@ -570,7 +570,7 @@ def test_small_rooms_default_and_memo_equal_the_plain_scan(kernel):
 def test_memo_and_delta_on_wild_rooms_every_lane_width(kernel, oracle):
     """The memo form against the full scan, bit for bit, and the delta form against a fresh evaluation, on
     rooms with shared clearance sources, relationship hubs, frozen objects and odd sizes, for every lane
-    width (32 lanes = the variant that also memoises the clearance row sums)."""
+    width."""
     for seed in range(10):
         g = np.random.default_rng(7000 + seed)
         n = int(g.integers(1, 70))

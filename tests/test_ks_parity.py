@@ -87,7 +87,7 @@ def test_config3_long_horizon_against_committed_oracle_samples(kernel):
 
 
 def test_config4_against_committed_oracle_samples(kernel):
-    """200 objects (the default runs the memo form with clearance row sums, 32 lanes per chain): 4096 chains x 100
+    """200 objects (the default runs the memo form, 32 lanes per chain): 4096 chains x 100
     iterations, default and delta evaluation."""
     z = fixture()
     chains, iters = (int(v) for v in z["cfg4_plan"])
