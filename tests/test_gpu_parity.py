@@ -739,3 +739,49 @@ def test_full_size_properties_config4(kernel, oracle):
     lay = layouts_from_points(room, pts[sub])
     assert_costs_close(room, costs[sub], oracle.costs_batch(room, lay), skip_pair=near_jump(oracle, room, lay))
     assert len(np.unique(costs["totalCosts"])) > 1000
+
+
+def _shifted(room, dx, dy):
+    """The same room translated by (dx, dy): surface, layout, centroid and focal point move together."""
+    import copy
+    r = copy.deepcopy(room)
+    r.surfaceRectangle["x"] += dx
+    r.surfaceRectangle["y"] += dy
+    r.cfg["x"] += dx
+    r.cfg["y"] += dy
+    for f, d in (("centroidX", dx), ("centroidY", dy), ("focalX", dx), ("focalY", dy)):
+        r.srf[f] += d
+    return r
+
+
+def test_integer_clearance_sum_at_extreme_scales(kernel, oracle):
+    """ClearanceCosts (Kernel.cu:404-434) is computed as an exact integer sum whose fixed-point scale the host picks
+    from the room (kernel_wrapper.c, clearance_scale): nothing may overflow or lose more than float32 already loses
+    when the room is tiny (every rectangle covers it: the largest possible sum per unit of area), huge, far from the
+    origin, or when all 200 objects of the hall sit on one point (the largest sum the accumulator must hold).
+    Tolerance: a float32 coordinate of magnitude M carries ulp(M)/2, and an overlap of unit-sized rectangles inherits
+    it relatively, so rtol = max(1e-5, 4 ulp(M)) -- the oracle's own float32 arithmetic is not better than that.
+    The memo form must return the plain scan's bytes whatever the scale."""
+    cases = [("tiny room", S.make_room(40, 40, 10, 0.05, 0.04, 31), 0.05),
+             ("huge room", S.make_room(60, 30, 20, 5000.0, 4000.0, 32), 5000.0),
+             ("far from the origin", _shifted(S.make_room(50, 25, 50, 8.0, 6.0, 33), 900.0, -700.0), 910.0),
+             ("hall", S.make_config(4), 20.0)]
+    for name, room, mag in cases:
+        n = room.n
+        lay = S.random_layouts(room, 48, 77)
+        piled = np.tile(room.cfg, 1)
+        piled["x"], piled["y"] = np.float32(room.surfaceRectangle["x"].mean()), np.float32(room.surfaceRectangle["y"].mean())
+        both = np.zeros(len(lay) + n, L.positionAndRotation)    # (np.concatenate would drop the padded 72-byte dtype)
+        both[:len(lay)], both[len(lay):] = lay, piled
+        lay = both
+        got = kernel.eval_costs(room, lay)
+        ref = oracle.costs_batch(room, lay)
+        assert np.isfinite(got["totalCosts"]).all(), name
+        rtol = max(1e-5, 4 * float(np.spacing(np.float32(mag))))
+        g, r = got["ClearanceCosts"].astype(np.float64), ref["ClearanceCosts"].astype(np.float64)
+        floor = rtol * abs(float(room.srf["WeightClearance"][0])) * room.C
+        assert np.all(np.abs(g - r) <= rtol * np.abs(r) + floor), (name, float(np.abs(g - r).max()), float(np.abs(r).max()))
+        assert abs(g[-1] - r[-1]) <= rtol * abs(r[-1]) + floor and abs(r[-1]) > 0, (name, "piled", g[-1], r[-1])
+        a = kernel.wrapper_ex(room, 96, 120, seed=5, eval_mode=2)
+        b = kernel.wrapper_ex(room, 96, 120, seed=5, eval_mode=3)
+        assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes(), name
